@@ -1,0 +1,380 @@
+#!/usr/bin/env python
+"""bench.py — RAS outer iterations per second on BASELINE.json configs[1]:
+2-D 5-pt Laplacian 8192x8192, fp64/int32, 8 subdomains (1-D strips,
+--partition=regular), CG local solve with a fixed budget of --local-iters
+iterations, synchronous halo exchange, global convergence check.
+
+A "step" is one outer RAS iteration over all 8 subdomains: halo exchange ->
+boundary update -> residual check (+ allgather) -> local CG solve ->
+restriction (source/schwarz_base.cpp:387-452 of the reference).  The 8
+subdomains are spread over the N GPUs (8/N per GPU), so the problem — and the
+sequence of iterates — is the same at every N ("strong" scaling).
+
+    python bench.py --gpus N --steps K --warmup W
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference ...      # CPU arm (oracle port on the host cores)
+
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "schwarz-lib_b200"))
+
+METRIC = "ras_outer_iters_per_s"
+UNIT = "outer iters/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n", type=int, default=8192, help="1-D Laplacian size (grid is n x n)")
+    ap.add_argument("--subdomains", type=int, default=8)
+    ap.add_argument("--local-iters", type=int, default=50, help="--local_max_iters of bench_ras")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def workload(args):
+    return {
+        "workload": "cfg2: 2D 5-pt Laplacian %dx%d fp64/int32, %d subdomains (regular 1-D strips, "
+                    "overlap 2), CG local solve local_max_iters=%d local_tol=1e-12, synchronous "
+                    "halo exchange, enable_global_check" % (args.n, args.n, args.subdomains,
+                                                            args.local_iters),
+        "n": args.n, "subdomains": args.subdomains, "local_max_iters": args.local_iters,
+        "overlap": 2, "partition": "regular",
+        "l2_policy": "inputs larger than L2 (each local CSR is ~0.5 GB vs 126 MB L2)",
+    }
+
+
+# ----------------------------------------------------------------------------
+# clocks during the timed region (B200_PROFILING.md recipe)
+# ----------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                 "--format=csv,noheader,nounits", "-lms", "200"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                  "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": max(smax) if smax else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------
+# CPU arm: the oracle port (oracle/schwz_oracle.cpp) on the host cores.  The
+# reference binary cannot be built here (MPI + Ginkgo expt-develop + gflags),
+# see DESIGN.md, so kind = "port".
+# ----------------------------------------------------------------------------
+_CPU_CACHE = {}
+
+
+def cpu_sample(args, steps=1):
+    """One bounded sample = the local solve of ONE of the `subdomains` strips
+    (local_max_iters CG iterations on its local matrix) plus its residual-check
+    SpMV, with every host core; an outer iteration costs `subdomains` of those,
+    so iters/s = 1 / (subdomains * t_sample).  Input: the strip's local CSR as
+    produced by the product's host setup (bit-identical to the oracle's,
+    tests/test_setup.py)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle as O
+    import schwz_b200 as S
+    cores = O.max_threads()
+    O.set_threads(cores)
+    key = (args.n, args.subdomains)
+    if key not in _CPU_CACHE:
+        setup = S.Setup(("laplacian2d", args.n), args.subdomains)
+        r = min(1, args.subdomains - 1)          # an interior strip when there is one
+        _CPU_CACHE[key] = setup.local_matrix(r)
+        del setup
+    rp, ci, v = _CPU_CACHE[key]
+    n = len(rp) - 1
+    b = np.ones(n)
+    x = np.zeros(n)
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        O.spmv(rp, ci, v, x, -1.0, 1.0, b)                       # residual check (A10)
+        x, it = O.cg(rp, ci, v, b, x, args.local_iters, 1e-12)   # local solve (A12)
+        times.append(time.perf_counter() - t0)
+    t = float(np.median(times))
+    value = 1.0 / (args.subdomains * t)
+    return {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "1 of %d strips: residual SpMV + %d CG iterations on its %d-row local "
+                      "matrix, %.2f s per sample, scaled x%d" % (args.subdomains, args.local_iters,
+                                                                 n, t, args.subdomains)}, t
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    t_all = []
+    base = None
+    for i in range(args.warmup + args.steps):
+        base, t = cpu_sample(args, steps=1)
+        if i >= args.warmup:
+            t_all.append(t)
+        if sum(t_all) > 150:
+            break
+    t = float(np.mean(t_all))
+    value = 1.0 / (args.subdomains * t)
+    base["value"] = value
+    out = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
+           "n_gpus": args.gpus, "steps": len(t_all), "warmup": args.warmup,
+           "ms_per_step": 1e3 * args.subdomains * t, "higher_is_better": True,
+           "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": workload(args), "cpu_baseline": base,
+           "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out))
+
+
+# ----------------------------------------------------------------------------
+# B200 arm
+# ----------------------------------------------------------------------------
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import schwz_b200 as S
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node == --gpus"
+    P = args.subdomains
+    assert P % world == 0, "subdomains must divide evenly over the GPUs"
+    nl = P // world
+    my = list(range(rank * nl, (rank + 1) * nl))
+    dev = local_rank if world > 1 else 0
+    torch.cuda.set_device(dev)
+
+    # ---- setup (host index sets, upload) — outside every timed region --------
+    setup = S.Setup(("laplacian2d", args.n), P)
+    ctxs = [S.Context(dev) for _ in my]
+    subs = []
+    for c, r in zip(ctxs, my):
+        subs.append(S.Ras(c, setup, r, tolerance=1e-6, local_tol=1e-12,
+                          local_max_iters=args.local_iters))
+        setup.release(r)
+    S.connect_local(subs, setup)
+    comm = None
+    imported = {}
+    if world > 1:
+        # exchange mailbox IPC handles + layouts + in-neighbour lists
+        mine = {}
+        for s in subs:
+            base, lay = s.mailbox()
+            mine[s.rank] = (s.ctx.ipc_export(base), lay.as_tuple(), s.neighbors()[0].tolist())
+        allinfo = [None] * world
+        dist.all_gather_object(allinfo, mine)
+        info = {}
+        for d in allinfo:
+            info.update(d)
+        for s in subs:
+            _, nout = s.neighbors()
+            pd, _ = setup.displacements(s.rank)
+            for j, q in enumerate(nout.tolist()):
+                if q in my:
+                    continue
+                handle, lay, q_in = info[q]
+                if q not in imported:
+                    imported[q] = s.ctx.ipc_import(handle)
+                s.connect(j, imported[q], S.MailboxLayout.from_tuple(lay), int(pd[q]),
+                          q_in.index(s.rank), same_process=False)
+        uid = [S.Comm.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        comm = S.Comm(ctxs[0], uid[0], world, rank)
+
+    def barrier():
+        for s in subs:
+            s.sync()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def run_steps(k):
+        return S.ras_run(subs, P, k, tolerance=1e-6, enable_global_check=True, comm=comm)
+
+    # ---- warm-up, then exactly K timed steps ---------------------------------
+    barrier()
+    if args.warmup > 0:
+        run_steps(args.warmup)
+    barrier()
+    sampler = ClockSampler(dev)
+    if rank == 0:
+        sampler.start()
+    launches0 = S.launch_count()
+    for c in ctxs:
+        c.timer_start()                 # CUDA event on every subdomain's stream
+    t0 = time.perf_counter()
+    res = run_steps(args.steps)
+    ms = max(c.timer_stop() for c in ctxs)   # device time, max over the local streams
+    wall = time.perf_counter() - t0
+    barrier()
+    launches = S.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([ms, float(launches)], dtype=torch.float64, device="cuda")
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        ms = float(tmax[0])
+        launches = int(t[1])
+    value = args.steps / (ms * 1e-3)
+
+    # ---- roofline of the dominant kernel (CG SpMV with fused dot) ------------
+    s0 = subs[min(1, len(subs) - 1)]
+    roof = {}
+    kern = {}
+    for kind, name in ((0, "csr_spmv_stream_kernel<EPI_DOT>"), (1, "cg_xr_update_kernel"),
+                       (2, "cg_p_update_kernel"), (3, "csr_spmv_stream_kernel<EPI_NRM2>")):
+        kms = s0.kernel_time_ms(kind, 20)
+        kb = s0.kernel_bytes(kind)
+        kern[name] = {"ms": kms, "bytes": kb, "GB/s": kb / (kms * 1e-3) / 1e9}
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak = float(json.load(open(peaks_path))["hbm_gbs"])
+        peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)"
+    else:
+        peak, peak_src = 6650.0, "B200_PROFILING.md fallback (of fallback)"
+    k0 = kern["csr_spmv_stream_kernel<EPI_DOT>"]
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "spmv_traffic.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+    per_step_spmv_ms = k0["ms"] * args.local_iters * nl
+    roof = {"bound": "hbm", "kernel": "csr_spmv_stream_kernel<EPI_DOT> (q = A p, p.q fused)",
+            "achieved": k0["GB/s"], "peak": peak, "unit": "GB/s", "frac": k0["GB/s"] / peak,
+            "traffic": traffic, "peak_source": peak_src, "bytes_per_launch": k0["bytes"],
+            "launch_ms": k0["ms"], "share_of_step": per_step_spmv_ms / (ms / args.steps),
+            "other_kernels": {k: v for k, v in kern.items() if k != "csr_spmv_stream_kernel<EPI_DOT>"}}
+
+    # ---- e2e: the plugin call with HOST buffers ------------------------------
+    # rhs (pinned host) -> device, zero initial state, K outer iterations (each
+    # reads the residual norms back, as the reference does), solution -> host.
+    e2e = None
+    if not args.no_e2e:
+        N = args.n * args.n
+        rhs = torch.ones(N, dtype=torch.float64).pin_memory()
+        sol = torch.zeros(N, dtype=torch.float64).pin_memory()
+        barrier()
+        t0 = time.perf_counter()
+        for s in subs:
+            s.upload_rhs(rhs.data_ptr())
+            s.reset()
+        r2 = run_steps(args.steps)
+        for s in subs:
+            s.download_solution(sol.data_ptr())
+        barrier()
+        te = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([te], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            te = float(t[0])
+        h2d = sum(s.local_size_x for s in subs) * 8
+        d2h = sum(s.local_size for s in subs) * 8
+        if world > 1:
+            t = torch.tensor([h2d, d2h], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            h2d, d2h = int(t[0]), int(t[1])
+        e2e = {"value": args.steps / te, "unit": UNIT,
+               "h2d_bytes_per_step": h2d / args.steps,
+               "d2h_bytes_per_step": d2h / args.steps + 8 * P,
+               "note": "schwz_b200_ras_upload_rhs + ras_reset + ras_run(K) + "
+                       "ras_download_solution with pinned host buffers; rhs/solution copies "
+                       "amortised over the K steps, residual norms read back every step"}
+
+    # ---- CPU baseline beside it (rank 0, N == 1 only) ------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            cpu, _ = cpu_sample(args, steps=3)
+        except Exception as e:  # the oracle is only a reported baseline
+            cpu = {"value": None, "unit": UNIT, "cores": None, "kind": "port",
+                   "sample": "failed: %r" % (e,)}
+
+    if rank == 0:
+        out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+               "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+               "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+               "dtype": "f64", "data": "synthetic", "config": workload(args),
+               "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof,
+               "cpu_baseline": cpu, "wall_ms_per_step": 1e3 * wall / args.steps,
+               "global_resnorm": res["global_resnorm"], "impl": "b200"}
+        print(json.dumps(out))
+
+    for s in subs:
+        s.close()
+    if comm is not None:
+        comm.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,126 @@
+// Internal C++ layer under the C ABI: device context, CSR container, kernel
+// launchers.  Nothing here is exported; include/schwz_b200.h is the boundary.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <vector>
+
+#include "common.cuh"
+
+namespace schwz_b200 {
+
+struct Ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    double *partials = nullptr;        // kMaxPartials doubles
+    unsigned int *tickets = nullptr;   // 16 tickets, zero-initialised
+    double *dev_scalars = nullptr;     // 16 doubles of scratch
+    double *pinned = nullptr;          // 16 doubles, host-pinned
+    cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
+
+    explicit Ctx(int dev);
+    ~Ctx();
+    void use() const { SCHWZ_CUDA(cudaSetDevice(device)); }
+    void sync() const
+    {
+        use();
+        SCHWZ_CUDA(cudaStreamSynchronize(stream));
+    }
+    template <typename T>
+    T *alloc(size_t n) const
+    {
+        use();
+        void *p = nullptr;
+        SCHWZ_CUDA(cudaMalloc(&p, (n ? n : 1) * sizeof(T)));
+        return (T *)p;
+    }
+    template <typename T>
+    T *alloc_zero(size_t n) const
+    {
+        T *p = alloc<T>(n);
+        SCHWZ_CUDA(cudaMemsetAsync(p, 0, (n ? n : 1) * sizeof(T), stream));
+        return p;
+    }
+    template <typename T>
+    T *upload(const T *host, size_t n) const
+    {
+        T *p = alloc<T>(n);
+        if (n) SCHWZ_CUDA(cudaMemcpyAsync(p, host, n * sizeof(T), cudaMemcpyHostToDevice, stream));
+        SCHWZ_CUDA(cudaStreamSynchronize(stream));
+        return p;
+    }
+    void release(void *p) const
+    {
+        if (p) {
+            use();
+            cudaFree(p);
+        }
+    }
+};
+
+// Device CSR + the row tiling used by the streaming SpMV: CTA b owns rows
+// [blk_row[b], blk_row[b+1]) with at most kBlock rows and (unless it is a
+// single long row) at most kSpmvTile non-zeros.
+struct DeviceCsr {
+    const Ctx *ctx = nullptr;
+    int32_t nrows = 0, ncols = 0;
+    int64_t nnz = 0;
+    int32_t *rp = nullptr, *ci = nullptr;
+    double *v = nullptr;
+    int32_t nblocks = 0;
+    int32_t *blk_row = nullptr;
+    ~DeviceCsr();
+};
+
+DeviceCsr *csr_upload(const Ctx &ctx, int32_t nrows, int32_t ncols, const int32_t *rp,
+                      const int32_t *ci, const double *v);
+
+// scalars of one device-resident Krylov solve
+struct CgScalars {
+    double rho, prev_rho, beta, r0, resnorm, tol;
+    int32_t iter, stop, max_iters, pad;
+};
+
+enum SpmvEpilogue { EPI_NONE = 0, EPI_DOT = 1, EPI_NRM2SQ = 2, EPI_NRM2 = 3 };
+
+// y_out = alpha*A*x + beta*y_in  (+ fused reduction over rows < red_rows).
+// stop: optional device flag; the launch is a no-op when *stop != 0.
+void launch_spmv(const Ctx &ctx, const DeviceCsr &A, double alpha, const double *x,
+                 double beta, const double *y_in, double *y_out, SpmvEpilogue epi,
+                 const double *dot_with, double *result, int32_t red_rows,
+                 const int32_t *stop);
+
+void launch_dot(const Ctx &ctx, int64_t n, const double *a, const double *b, double *result,
+                bool sqrt_result);
+void launch_axpy(const Ctx &ctx, int64_t n, double alpha, const double *x, double *y);
+void launch_copy(const Ctx &ctx, int64_t n, const double *src, double *dst);
+void launch_gather(const Ctx &ctx, int32_t n, const int32_t *idx, const double *from,
+                   double *into, int op);
+void launch_scatter(const Ctx &ctx, int32_t n, const int32_t *idx, const double *from,
+                    double *into, int op);
+void launch_permute(const Ctx &ctx, int32_t n, const int32_t *perm, int inverse,
+                    const double *in, double *out);
+
+// CG step kernels (Ginkgo Cg semantics)
+void launch_cg_init(const Ctx &ctx, CgScalars *s, int32_t max_iters, double tol,
+                    const int32_t *outer_stop);
+void launch_cg_p_update(const Ctx &ctx, int64_t n, const double *r, double *p, const CgScalars *s);
+void launch_cg_xr_update(const Ctx &ctx, int64_t n, double *x, double *r, const double *p,
+                         const double *q, CgScalars *s);
+
+// halo
+void launch_halo_pack_push(const Ctx &ctx, int32_t nseg, const int32_t *seg_off_dev,
+                           int32_t total, const int32_t *src_idx, const double *x,
+                           double *const *dst_ptrs, unsigned long long *const *flag_ptrs,
+                           unsigned long long epoch, const int32_t *stop);
+void launch_halo_unpack(const Ctx &ctx, int32_t nseg, int32_t total, const int32_t *dst_idx,
+                        const double *recv, double *x, const unsigned long long *flags,
+                        unsigned long long epoch, int32_t *error_flag);
+
+// convergence flags (include/conv_tools.hpp:248-274 on peer-mapped words)
+void launch_conv_forward(const Ctx &ctx, int32_t P, int32_t me, int32_t converged_all_local,
+                         int32_t *conv, int32_t *conv_sent, int32_t n_out,
+                         int32_t *const *peer_conv, int32_t *num_converged);
+
+}  // namespace schwz_b200

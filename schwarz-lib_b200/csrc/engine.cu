@@ -1,0 +1,612 @@
+// Per-subdomain state of the RAS iteration, the stages of the outer loop and
+// the loop itself (replaces SchwarzBase::run's loop body,
+// source/schwarz_base.cpp:387-452, and everything it calls).
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cfloat>
+#include <cstring>
+
+#include "engine.hpp"
+
+namespace schwz_b200 {
+
+// =============================================================================
+// NCCL through dlopen: the only collective on the path is the allgather of P
+// residual norms (MPI_Allgather, source/solve.cpp:890-891).  Loading lazily
+// keeps the library loadable where NCCL is absent and binds to whichever
+// libnccl.so.2 the process already carries (torch's, under torchrun).
+// =============================================================================
+namespace {
+struct Id128 {   // ncclUniqueId is passed by value: 128 bytes
+    char b[128];
+};
+struct NcclApi {
+    void *h = nullptr;
+    int (*GetUniqueId)(void *) = nullptr;
+    int (*CommInitRank)(void **, int, Id128, int) = nullptr;
+    int (*AllGather)(const void *, void *, size_t, int, void *, cudaStream_t) = nullptr;
+    int (*CommDestroy)(void *) = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+};
+NcclApi &nccl()
+{
+    static NcclApi api;
+    if (!api.h) {
+        api.h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!api.h) api.h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        SCHWZ_REQUIRE(api.h != nullptr, "cannot load libnccl.so.2");
+        api.GetUniqueId = (int (*)(void *))dlsym(api.h, "ncclGetUniqueId");
+        api.CommInitRank = (int (*)(void **, int, Id128, int))dlsym(api.h, "ncclCommInitRank");
+        api.AllGather = (int (*)(const void *, void *, size_t, int, void *, cudaStream_t))dlsym(
+            api.h, "ncclAllGather");
+        api.CommDestroy = (int (*)(void *))dlsym(api.h, "ncclCommDestroy");
+        api.GetErrorString = (const char *(*)(int))dlsym(api.h, "ncclGetErrorString");
+        SCHWZ_REQUIRE(api.GetUniqueId && api.CommInitRank && api.AllGather && api.CommDestroy,
+                      "libnccl lacks the expected symbols");
+    }
+    return api;
+}
+void nccl_check(int rc, const char *what)
+{
+    if (rc != 0) {
+        const char *s = nccl().GetErrorString ? nccl().GetErrorString(rc) : "?";
+        throw std::runtime_error(std::string("NCCL ") + what + ": " + s);
+    }
+}
+}  // namespace
+
+void comm_unique_id(void *id128) { nccl_check(nccl().GetUniqueId(id128), "ncclGetUniqueId"); }
+
+Comm *comm_create(const Ctx &ctx, const void *id128, int nranks, int rank)
+{
+    ctx.use();
+    auto *c = new Comm();
+    c->ctx = &ctx;
+    c->nranks = nranks;
+    c->rank = rank;
+    Id128 id;
+    std::memcpy(&id, id128, sizeof(id));
+    nccl_check(nccl().CommInitRank(&c->nccl, nranks, id, rank), "ncclCommInitRank");
+    return c;
+}
+
+Comm::~Comm()
+{
+    if (nccl) ::schwz_b200::nccl().CommDestroy(nccl);
+    if (ctx) {
+        ctx->release(dev_in);
+        ctx->release(dev_out);
+    }
+}
+
+void comm_allgather_f64(Comm &c, const double *dev_in, int count, double *dev_out)
+{
+    c.ctx->use();
+    // ncclDouble == 8
+    nccl_check(nccl().AllGather(dev_in, dev_out, (size_t)count, 8, c.nccl, c.ctx->stream),
+               "ncclAllGather");
+}
+
+// =============================================================================
+// Mailbox
+// =============================================================================
+static int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
+
+MailboxLayout MailboxLayout::make(int64_t in_total, int32_t n_in, int32_t P)
+{
+    MailboxLayout m;
+    m.recv_stride = align_up(std::max<int64_t>(in_total, 1) * 8, 256);
+    m.flags_off = 2 * m.recv_stride;
+    m.conv_off = m.flags_off + align_up(std::max(n_in, 1) * 8, 256);
+    m.err_off = m.conv_off + align_up((int64_t)std::max(P, 3) * 4, 256);
+    m.bytes = m.err_off + 256;
+    return m;
+}
+
+// =============================================================================
+// Ras
+// =============================================================================
+Ras::Ras(const Ctx &ctx_, Setup &setup, int32_t rank_, const double *host_rhs_global,
+         const RasOptions &opt_)
+    : ctx(ctx_), rank(rank_), P(setup.P()), opt(opt_)
+{
+    setup.build_matrices(rank);
+    RankLayout &R = setup.rank(rank);
+    local_size = R.local_size;
+    local_size_x = R.local_size_x;
+    overlap_size = R.overlap_size;
+    n_halo = R.n_halo;
+    first_row = setup.first_row()[rank];
+    nbr_in = R.nbr_in;
+    nbr_out = R.nbr_out;
+    local_nnz = R.local.nnz();
+    ctx.use();
+
+    A.reset(csr_upload(ctx, R.local.nrows, R.local.ncols, R.local.rp.data(), R.local.ci.data(),
+                       R.local.v.data()));
+    HostCsr Ic;
+    setup.compact_interface(rank, Ic);
+    I.reset(csr_upload(ctx, Ic.nrows, Ic.ncols, Ic.rp.data(), Ic.ci.data(), Ic.v.data()));
+
+    l2g_local_.assign(R.l2g.begin(), R.l2g.begin() + local_size_x);
+    // A6: local_rhs = [rhs[own] ; rhs[overlap_row]]  (initialization.cpp:333-359)
+    std::vector<double> lrhs((size_t)local_size_x, 1.0);
+    if (host_rhs_global)
+        for (int32_t k = 0; k < local_size_x; ++k) lrhs[k] = host_rhs_global[R.l2g[k]];
+    local_rhs = ctx.upload(lrhs.data(), lrhs.size());
+    // F8: the reference leaves these uninitialised and relies on zeros
+    x = ctx.alloc_zero<double>((size_t)local_size_x + n_halo);
+    local_sol = ctx.alloc_zero<double>(local_size_x);
+    init_guess = ctx.alloc_zero<double>(local_size_x);
+    work = ctx.alloc_zero<double>(2 * (size_t)local_size_x);
+    resnorm_dev = ctx.alloc_zero<double>(2);
+    num_converged_dev = ctx.alloc_zero<int32_t>(2);
+    conv_sent = ctx.alloc_zero<int32_t>(std::max(P, 3));
+
+    // halo tables.  in: scatter targets in compact numbering (g2l - 1);
+    // out: gather sources inside my own block (global id - first_row).
+    std::vector<int32_t> pos_of;   // global id -> compact slot for the non-own part
+    {
+        // ids beyond local_size appear once in l2g; binary search on a sorted copy
+        std::vector<std::pair<int32_t, int32_t>> ext;
+        ext.reserve(R.l2g.size() - local_size);
+        for (int32_t k = local_size; k < (int32_t)R.l2g.size(); ++k) ext.emplace_back(R.l2g[k], k);
+        std::sort(ext.begin(), ext.end());
+        std::vector<int32_t> dst;
+        for (size_t j = 0; j < R.get.size(); ++j) {
+            in_count.push_back((int32_t)R.get[j].size());
+            for (int32_t gid : R.get[j]) {
+                auto it = std::lower_bound(ext.begin(), ext.end(), std::make_pair(gid, (int32_t)-1));
+                SCHWZ_REQUIRE(it != ext.end() && it->first == gid, "halo id not in the index set");
+                dst.push_back(it->second);
+            }
+        }
+        in_total_ = (int32_t)dst.size();
+        in_dst_ = ctx.upload(dst.data(), dst.size());
+    }
+    {
+        std::vector<int32_t> src, off(1, 0);
+        for (size_t j = 0; j < R.put.size(); ++j) {
+            out_count.push_back((int32_t)R.put[j].size());
+            for (int32_t gid : R.put[j]) src.push_back(gid - first_row);
+            off.push_back((int32_t)src.size());
+        }
+        out_total_ = (int32_t)src.size();
+        out_src_ = ctx.upload(src.data(), src.size());
+        out_off_ = ctx.upload(off.data(), off.size());
+    }
+    mbox = MailboxLayout::make(in_total_, (int32_t)nbr_in.size(), P);
+    mailbox = ctx.alloc_zero<char>((size_t)mbox.bytes);
+    const size_t no = nbr_out.size();
+    for (int b = 0; b < 2; ++b) out_dst_host_[b].assign(no, nullptr);
+    out_flag_host_.assign(no, nullptr);
+    out_conv_host_.assign(no, nullptr);
+    out_same_process_.assign(no, 1);
+    for (int b = 0; b < 2; ++b) out_dst_dev_[b] = ctx.alloc_zero<double *>(std::max<size_t>(no, 1));
+    out_flag_dev_ = ctx.alloc_zero<unsigned long long *>(std::max<size_t>(no, 1));
+    out_conv_dev_ = ctx.alloc_zero<int32_t *>(std::max<size_t>(no, 1));
+    SCHWZ_CUDA(cudaEventCreateWithFlags(&ev_pushed, cudaEventDisableTiming));
+
+    if (opt.local_solver == 2) {
+        if (opt.non_symmetric) gmres.reset(new GmresSolver(ctx, *A, opt.restart_iter));
+        else cg.reset(new CgSolver(ctx, *A));
+    }
+    ctx.sync();
+}
+
+Ras::~Ras()
+{
+    cudaSetDevice(ctx.device);
+    cudaStreamSynchronize(ctx.stream);
+    for (void *p : {(void *)x, (void *)local_rhs, (void *)local_sol, (void *)init_guess,
+                    (void *)work, (void *)resnorm_dev, (void *)num_converged_dev,
+                    (void *)conv_sent, (void *)mailbox, (void *)in_dst_, (void *)out_src_,
+                    (void *)out_off_, (void *)out_dst_dev_[0], (void *)out_dst_dev_[1],
+                    (void *)out_flag_dev_, (void *)out_conv_dev_, (void *)fperm})
+        ctx.release(p);
+    if (ev_pushed) cudaEventDestroy(ev_pushed);
+    if (pinned_rhs_) cudaFreeHost(pinned_rhs_);
+}
+
+void Ras::upload_rhs(const double *host_rhs_global)
+{
+    ctx.use();
+    if (!pinned_rhs_)
+        SCHWZ_CUDA(cudaMallocHost((void **)&pinned_rhs_, sizeof(double) * (size_t)local_size_x));
+    // own block is contiguous in the global numbering; overlap rows are gathered
+    std::memcpy(pinned_rhs_, host_rhs_global + first_row, sizeof(double) * (size_t)local_size);
+    for (int32_t k = local_size; k < local_size_x; ++k) pinned_rhs_[k] = host_rhs_global[l2g_local_[k]];
+    SCHWZ_CUDA(cudaMemcpyAsync(local_rhs, pinned_rhs_, sizeof(double) * (size_t)local_size_x,
+                               cudaMemcpyHostToDevice, ctx.stream));
+}
+
+void Ras::download_solution(double *host_solution_global)
+{
+    ctx.use();
+    SCHWZ_CUDA(cudaMemcpyAsync(host_solution_global + first_row, x, sizeof(double) * (size_t)local_size,
+                               cudaMemcpyDeviceToHost, ctx.stream));
+}
+
+void Ras::reset_state()
+{
+    ctx.use();
+    SCHWZ_CUDA(cudaMemsetAsync(x, 0, sizeof(double) * ((size_t)local_size_x + n_halo), ctx.stream));
+    SCHWZ_CUDA(cudaMemsetAsync(init_guess, 0, sizeof(double) * (size_t)local_size_x, ctx.stream));
+    SCHWZ_CUDA(cudaMemsetAsync(local_sol, 0, sizeof(double) * (size_t)local_size_x, ctx.stream));
+    SCHWZ_CUDA(cudaMemsetAsync(conv(), 0, sizeof(int32_t) * (size_t)std::max(P, 3), ctx.stream));
+    SCHWZ_CUDA(cudaMemsetAsync(conv_sent, 0, sizeof(int32_t) * (size_t)std::max(P, 3), ctx.stream));
+    resnorm = resnorm0 = -1.0;
+    gres = 0.0;
+    gres0 = -1.0;
+    num_converged = 0;
+    finished = false;
+    finished_iter = -1;
+}
+
+float Ras::kernel_time_ms(int kind, int reps)
+{
+    ctx.use();
+    double *p = work, *q = work + local_size_x;
+    // warm-up launch, then `reps` timed launches back to back
+    auto one = [&]() {
+        switch (kind) {
+        case 0:
+            launch_spmv(ctx, *A, 1.0, p, 0.0, nullptr, q, EPI_DOT, p, resnorm_dev + 1, local_size_x,
+                        nullptr);
+            break;
+        case 3:
+            launch_spmv(ctx, *A, -1.0, x, 1.0, local_sol, q, EPI_NRM2, nullptr, resnorm_dev + 1,
+                        local_size_x, nullptr);
+            break;
+        case 4:
+            exchange_push(0);
+            exchange_unpack(0, false);
+            break;
+        default: SCHWZ_REQUIRE(cg != nullptr, "no CG solver on this subdomain"); cg->bench_step(kind, work);
+        }
+    };
+    one();
+    SCHWZ_CUDA(cudaEventRecord(ctx.ev_start, ctx.stream));
+    for (int i = 0; i < reps; ++i) one();
+    SCHWZ_CUDA(cudaEventRecord(ctx.ev_stop, ctx.stream));
+    SCHWZ_CUDA(cudaEventSynchronize(ctx.ev_stop));
+    float ms = 0.f;
+    SCHWZ_CUDA(cudaEventElapsedTime(&ms, ctx.ev_start, ctx.ev_stop));
+    return ms / (float)reps;
+}
+
+void Ras::set_factors(const int32_t *Lrp, const int32_t *Lci, const double *Lv,
+                      const int32_t *perm)
+{
+    // U = L^T (source/solve.cpp:286-304)
+    HostCsr L;
+    L.nrows = L.ncols = local_size_x;
+    L.rp.assign(Lrp, Lrp + local_size_x + 1);
+    L.ci.assign(Lci, Lci + Lrp[local_size_x]);
+    L.v.assign(Lv, Lv + Lrp[local_size_x]);
+    HostCsr U = transpose(L);
+    Ltrs.reset(new TrsPlan(ctx, local_size_x, L.rp.data(), L.ci.data(), L.v.data(), false));
+    Utrs.reset(new TrsPlan(ctx, local_size_x, U.rp.data(), U.ci.data(), U.v.data(), true));
+    std::vector<int32_t> pv(local_size_x);
+    for (int32_t i = 0; i < local_size_x; ++i) pv[i] = perm ? perm[i] : i;
+    ctx.release(fperm);
+    fperm = ctx.upload(pv.data(), pv.size());
+}
+
+void Ras::connect(int32_t j, void *peer_base, const MailboxLayout &pl, int32_t peer_recv_offset,
+                  int32_t peer_flag_slot, bool same_process)
+{
+    SCHWZ_REQUIRE(j >= 0 && j < (int32_t)nbr_out.size(), "out-neighbour index out of range");
+    char *base = (char *)peer_base;
+    for (int b = 0; b < 2; ++b)
+        out_dst_host_[b][j] = (double *)(base + b * pl.recv_stride) + peer_recv_offset;
+    out_flag_host_[j] = (unsigned long long *)(base + pl.flags_off) + peer_flag_slot;
+    out_conv_host_[j] = (int32_t *)(base + pl.conv_off);
+    out_same_process_[j] = same_process ? 1 : 0;
+    peer_tables_dirty_ = true;
+}
+
+void Ras::upload_peer_tables()
+{
+    if (!peer_tables_dirty_) return;
+    const size_t no = nbr_out.size();
+    any_remote_ = false;
+    for (size_t j = 0; j < no; ++j) {
+        SCHWZ_REQUIRE(out_dst_host_[0][j] != nullptr, "out-neighbour not connected");
+        if (!out_same_process_[j]) any_remote_ = true;
+    }
+    if (no) {
+        ctx.use();
+        for (int b = 0; b < 2; ++b)
+            SCHWZ_CUDA(cudaMemcpyAsync(out_dst_dev_[b], out_dst_host_[b].data(), no * sizeof(void *),
+                                       cudaMemcpyHostToDevice, ctx.stream));
+        SCHWZ_CUDA(cudaMemcpyAsync(out_flag_dev_, out_flag_host_.data(), no * sizeof(void *),
+                                   cudaMemcpyHostToDevice, ctx.stream));
+        SCHWZ_CUDA(cudaMemcpyAsync(out_conv_dev_, out_conv_host_.data(), no * sizeof(void *),
+                                   cudaMemcpyHostToDevice, ctx.stream));
+        SCHWZ_CUDA(cudaStreamSynchronize(ctx.stream));
+    }
+    peer_tables_dirty_ = false;
+}
+
+// A8 send side: pack x[own] for every out-neighbour and store it into the
+// neighbours' receive buffers (epoch parity selects the buffer), publish the
+// epoch.  The flag store is always made: a same-process neighbour ignores it.
+void Ras::exchange_push(int32_t iter)
+{
+    upload_peer_tables();
+    const int32_t no = (int32_t)nbr_out.size();
+    if (no > 0) {
+        // epochs count exchanges over the lifetime of the subdomain, so the
+        // loop may be entered repeatedly (warm-up + timed runs)
+        ++push_epoch_;
+        launch_halo_pack_push(ctx, no, out_off_, out_total_, out_src_, x,
+                              out_dst_dev_[push_epoch_ & 1], out_flag_dev_,
+                              (unsigned long long)push_epoch_, nullptr);
+    }
+    SCHWZ_CUDA(cudaEventRecord(ev_pushed, ctx.stream));
+    last_push_iter = iter;
+}
+
+void Ras::wait_push_of(const Ras &nbr)
+{
+    ctx.use();
+    SCHWZ_CUDA(cudaStreamWaitEvent(ctx.stream, nbr.ev_pushed, 0));
+}
+
+// A8 receive side: scatter the receive buffer of this epoch into the
+// overlap + halo slots of x.
+void Ras::exchange_unpack(int32_t iter, bool wait_flags)
+{
+    const int32_t ni = (int32_t)nbr_in.size();
+    if (ni == 0) return;
+    ++unpack_epoch_;
+    const double *recv = (const double *)(mailbox + (unpack_epoch_ & 1) * mbox.recv_stride);
+    const unsigned long long *flags =
+        wait_flags ? (const unsigned long long *)(mailbox + mbox.flags_off) : nullptr;
+    launch_halo_unpack(ctx, ni, in_total_, in_dst_, recv, x, flags,
+                       (unsigned long long)unpack_epoch_, err_word());
+}
+
+// A9: local_solution = local_rhs - I * x  (source/restricted_schwarz.cpp:992-1017)
+void Ras::update_boundary()
+{
+    launch_copy(ctx, local_size, local_rhs, local_sol);
+    if (overlap_size > 0) {
+        if (P > 1 && opt.overlap > 0 && I->nnz > 0)
+            launch_spmv(ctx, *I, -1.0, x, 1.0, local_rhs + local_size, local_sol + local_size,
+                        EPI_NONE, nullptr, nullptr, 0, nullptr);
+        else
+            launch_copy(ctx, overlap_size, local_rhs + local_size, local_sol + local_size);
+    }
+}
+
+// A10: r = local_solution - A_loc [x_own ; x_overlap], ||r||_2
+// (source/solve.cpp:828-843).  extract_local_vector is the identity in the
+// compact layout; the norm is fused into the SpMV.
+void Ras::local_residual()
+{
+    launch_spmv(ctx, *A, -1.0, x, 1.0, local_sol, work, EPI_NRM2, nullptr, resnorm_dev,
+                local_size_x, nullptr);
+}
+
+// A12 / A13 (source/solve.cpp:709-781)
+void Ras::local_solve()
+{
+    if (opt.local_solver == 2) {
+        const int32_t cap = opt.local_max_iters == -1 ? local_size_x : opt.local_max_iters;
+        if (opt.non_symmetric) gmres->solve(local_sol, init_guess, cap, opt.local_tol);
+        else cg->solve(local_sol, init_guess, cap, opt.local_tol);
+        // local_solution <- init_guess (:781) is folded into restrict_to_x,
+        // which reads init_guess directly; keep local_solution coherent for
+        // callers that inspect it
+        launch_copy(ctx, local_size_x, init_guess, local_sol);
+    } else {
+        SCHWZ_REQUIRE(Ltrs && Utrs && fperm, "direct local solve without factors");
+        double *perm_sol = work, *tmp = work + local_size_x;
+        launch_permute(ctx, local_size_x, fperm, 0, local_sol, perm_sol);
+        Ltrs->solve(perm_sol, tmp);
+        Utrs->solve(tmp, perm_sol);
+        launch_permute(ctx, local_size_x, fperm, 1, perm_sol, local_sol);
+    }
+}
+
+// A14: x[own] = local_solution[0 .. local_size)  (source/communicate.cpp:65-94)
+void Ras::restrict_to_x() { launch_copy(ctx, local_size, local_sol, x); }
+
+double Ras::true_residual_sq()
+{
+    // ||b_own - (A x)_own||^2 : own rows of the local matrix are complete rows
+    // of the global matrix (no entry is dropped when overlap >= 2)
+    launch_spmv(ctx, *A, -1.0, x, 1.0, local_rhs, work, EPI_NRM2SQ, nullptr, resnorm_dev + 1,
+                local_size, nullptr);
+    double out = 0.0;
+    SCHWZ_CUDA(cudaMemcpyAsync(&out, resnorm_dev + 1, sizeof(double), cudaMemcpyDeviceToHost,
+                               ctx.stream));
+    ctx.sync();
+    return out;
+}
+
+void Ras::conv_forward(int32_t converged_all_local)
+{
+    upload_peer_tables();
+    launch_conv_forward(ctx, P, rank, converged_all_local, conv(), conv_sent,
+                        (int32_t)nbr_out.size(), out_conv_dev_, num_converged_dev);
+}
+
+// =============================================================================
+// The outer loop over the subdomains of this process.  One host thread drives
+// all local subdomains stage by stage; every stage is asynchronous on the
+// subdomain's stream, and the only host synchronisation per outer iteration is
+// the read-back of the residual norms for the convergence decision — the same
+// point at which the reference copies its norm to the host
+// (source/solve.cpp:841-843).
+// =============================================================================
+void ras_run(std::vector<Ras *> &subs, const LoopOptions &o, LoopResult &res,
+             double *history)
+{
+    const int nl = (int)subs.size();
+    const int P = o.num_subdomains;
+    SCHWZ_REQUIRE(nl > 0, "no subdomains");
+    const bool multi_process = o.comm != nullptr && o.comm->nranks > 1;
+    if (!multi_process) SCHWZ_REQUIRE(nl == P, "all subdomains must be local without a communicator");
+    std::vector<double> l_res(P, 0.0), mine(nl, 0.0);
+    if (multi_process) {
+        Comm &c = *o.comm;
+        SCHWZ_REQUIRE(nl * c.nranks == P, "subdomains must be spread evenly over the processes");
+        if (c.cap < P) {
+            c.ctx->release(c.dev_in);
+            c.ctx->release(c.dev_out);
+            c.dev_in = c.ctx->alloc_zero<double>(nl);
+            c.dev_out = c.ctx->alloc_zero<double>(P);
+            c.cap = P;
+        }
+    }
+    // map rank -> local subdomain (for same-process event waits)
+    std::vector<Ras *> by_rank(P, nullptr);
+    for (Ras *r : subs) by_rank[r->rank] = r;
+    for (Ras *r : subs) r->ctx.sync();
+
+    auto t0 = std::chrono::steady_clock::now();
+    int iter = 0, alive = nl;
+    bool all_done = false;
+    for (; iter < o.max_iters && !all_done; ++iter) {
+        // ---- 0 boundary exchange -------------------------------------------
+        if (P > 1 && !(o.enable_onesided && iter == 0)) {   // one-sided skips iter 0 (:725)
+            for (Ras *r : subs)
+                if (!r->finished) r->exchange_push(iter);
+            for (Ras *r : subs) {
+                if (r->finished) continue;
+                bool remote = false;
+                for (int32_t p : r->nbr_in) {
+                    Ras *s = by_rank[p];
+                    if (s) {
+                        if (!o.enable_onesided && !s->finished) r->wait_push_of(*s);
+                    } else {
+                        remote = true;
+                    }
+                }
+                r->exchange_unpack(iter, remote && !o.enable_onesided);
+            }
+        }
+        // ---- 1 boundary update, 2 convergence check ------------------------
+        for (Ras *r : subs) {
+            if (r->finished) continue;
+            r->update_boundary();
+            r->local_residual();
+        }
+        for (int i = 0; i < nl; ++i) {
+            Ras *r = subs[i];
+            if (r->finished) continue;
+            r->ctx.use();
+            SCHWZ_CUDA(cudaMemcpyAsync(&mine[i], r->resnorm_dev, sizeof(double),
+                                       cudaMemcpyDeviceToHost, r->ctx.stream));
+        }
+        for (Ras *r : subs)
+            if (!r->finished) r->ctx.sync();
+        const double tol = o.tolerance;
+        for (int i = 0; i < nl; ++i) {
+            Ras *r = subs[i];
+            if (r->finished) continue;
+            r->resnorm = mine[i];
+            if (std::isnan(r->resnorm)) throw std::runtime_error("residual norm is NaN");
+            if (r->resnorm0 < 0.0) r->resnorm0 = r->resnorm;
+            if (history) history[(size_t)iter * nl + i] = r->resnorm;
+        }
+        const bool iter_cond =
+            o.iter_offset ? ((iter > (o.max_iters * 0.05)) || o.max_iters < 1000) : true;
+        if (!o.enable_onesided) {
+            // two-sided: allgather + ordered sum (source/solve.cpp:888-912)
+            if (multi_process) {
+                Comm &c = *o.comm;
+                c.ctx->use();
+                SCHWZ_CUDA(cudaMemcpyAsync(c.dev_in, mine.data(), nl * sizeof(double),
+                                           cudaMemcpyHostToDevice, c.ctx->stream));
+                comm_allgather_f64(c, c.dev_in, nl, c.dev_out);
+                SCHWZ_CUDA(cudaMemcpyAsync(l_res.data(), c.dev_out, P * sizeof(double),
+                                           cudaMemcpyDeviceToHost, c.ctx->stream));
+                c.ctx->sync();
+            } else {
+                for (int i = 0; i < nl; ++i) l_res[subs[i]->rank] = mine[i];
+            }
+            for (Ras *r : subs) {
+                int num_converged_p =
+                    (tol >= 0.0 && (r->resnorm * r->resnorm) / (r->resnorm0 * r->resnorm0) < tol * tol)
+                        ? 1 : 0;
+                if (tol > 0.0 && iter_cond) {
+                    int converged_all_local = 0;
+                    if (o.enable_global_check) {
+                        r->gres = 0.0;
+                        for (int j = 0; j < P; ++j) {
+                            if (l_res[j] != DBL_MAX) {
+                                r->gres += l_res[j];
+                            } else {
+                                r->gres = -1.0;
+                                break;
+                            }
+                        }
+                        if (r->gres >= 0.0) {
+                            if (r->gres0 < 0.0) r->gres0 = r->gres;
+                            if (r->gres / r->gres0 <= tol) converged_all_local++;
+                        }
+                        if (converged_all_local == 1) num_converged_p = P;
+                    } else {
+                        num_converged_p = 0;
+                    }
+                    r->num_converged = num_converged_p;
+                }
+                if (std::isnan(r->gres) || r->gres > 1e12)
+                    throw std::runtime_error("diverged");   // schwarz_base.cpp:424-428
+            }
+        } else {
+            // one-sided: local ratio test + flag protocol (source/solve.cpp:913-943)
+            std::vector<int32_t> counts(nl, 0);
+            for (int i = 0; i < nl; ++i) {
+                Ras *r = subs[i];
+                if (r->finished) continue;
+                if (!(tol > 0.0 && iter_cond)) continue;
+                const int cal = (r->resnorm / r->resnorm0 <= tol) ? 1 : 0;
+                r->conv_forward(cal);
+                r->ctx.use();
+                SCHWZ_CUDA(cudaMemcpyAsync(&counts[i], r->num_converged_dev, sizeof(int32_t),
+                                           cudaMemcpyDeviceToHost, r->ctx.stream));
+            }
+            for (int i = 0; i < nl; ++i) {
+                Ras *r = subs[i];
+                if (r->finished || !(tol > 0.0 && iter_cond)) continue;
+                r->ctx.sync();
+                r->num_converged = counts[i];
+            }
+        }
+        // ---- break test (:432-433), 3 local solve, 4 restriction ------------
+        for (Ras *r : subs) {
+            if (r->finished) continue;
+            if (r->num_converged == P) {
+                r->finished = true;
+                r->finished_iter = iter;
+                --alive;
+            }
+        }
+        if (alive == 0) {
+            all_done = true;
+            break;
+        }
+        for (Ras *r : subs) {
+            if (r->finished) continue;
+            r->local_solve();
+            r->restrict_to_x();
+        }
+    }
+    for (Ras *r : subs) r->ctx.sync();
+    auto t1 = std::chrono::steady_clock::now();
+    res.iters = iter;
+    res.converged = all_done ? 1 : 0;
+    res.global_resnorm = subs[0]->gres;
+    res.global_resnorm0 = subs[0]->gres0;
+    res.elapsed_s = std::chrono::duration<double>(t1 - t0).count();
+}
+
+}  // namespace schwz_b200

@@ -1,0 +1,203 @@
+// Device-resident local solvers and the per-subdomain state of the RAS
+// iteration.  Internal; the C ABI in include/schwz_b200.h wraps these.
+#pragma once
+#include <memory>
+#include <vector>
+
+#include "device.hpp"
+#include "setup.hpp"
+
+namespace schwz_b200 {
+
+// ---- NCCL (loaded lazily with dlopen; only the residual-norm allgather) ------
+struct Comm {
+    void *nccl = nullptr;   // ncclComm_t
+    const Ctx *ctx = nullptr;
+    int nranks = 1, rank = 0;
+    double *dev_in = nullptr, *dev_out = nullptr;   // scratch for small gathers
+    int cap = 0;
+    ~Comm();
+};
+void comm_unique_id(void *id128);
+Comm *comm_create(const Ctx &ctx, const void *id128, int nranks, int rank);
+void comm_allgather_f64(Comm &c, const double *dev_in, int count, double *dev_out);
+
+// ---- CG (Ginkgo Cg semantics; source/solve.cpp:469-478, 572-652, 746-754) ----
+class CgSolver {
+public:
+    CgSolver(const Ctx &ctx, const DeviceCsr &A);
+    ~CgSolver();
+    // x holds the warm start; asynchronous on ctx.stream.  outer_stop: optional
+    // device flag that turns the whole solve into a no-op.
+    void solve(const double *b, double *x, int32_t max_iters, double tol,
+               const int32_t *outer_stop = nullptr);
+    void result(int32_t *iters, double *resnorm, double *resnorm0);   // synchronises
+    int64_t bytes_per_iteration() const;
+    void bench_step(int kind, double *scratch_x);   // 1: x/r update, 2: p update (timing only)
+
+private:
+    void iteration(double *x);
+    const Ctx &ctx_;
+    const DeviceCsr &A_;
+    int64_t n_;
+    double *r_ = nullptr, *p_ = nullptr, *q_ = nullptr;
+    CgScalars *s_ = nullptr;
+    int32_t *pinned_stop_ = nullptr;   // 2 slots
+    cudaEvent_t ev_[2] = {nullptr, nullptr};
+};
+
+// ---- GMRES(m) (Ginkgo Gmres semantics; source/solve.cpp:486-567) -------------
+class GmresSolver {
+public:
+    GmresSolver(const Ctx &ctx, const DeviceCsr &A, int32_t restart);
+    ~GmresSolver();
+    void solve(const double *b, double *x, int32_t max_iters, double tol);
+    void result(int32_t *iters, double *resnorm, double *resnorm0);
+
+private:
+    const Ctx &ctx_;
+    const DeviceCsr &A_;
+    int64_t n_;
+    int32_t m_;
+    double *V_ = nullptr;    // (m+1) x n basis, row-major by vector
+    double *w_ = nullptr;
+    double *small_ = nullptr;   // Hessenberg, rotations, g, y and scalars
+    int32_t *pinned_stop_ = nullptr;
+    cudaEvent_t ev_[2] = {nullptr, nullptr};
+};
+
+// ---- level-scheduled sparse triangular solve ---------------------------------
+class TrsPlan {
+public:
+    TrsPlan(const Ctx &ctx, int32_t n, const int32_t *rp, const int32_t *ci, const double *v,
+            bool upper);
+    ~TrsPlan();
+    void solve(const double *b, double *x);
+    int32_t num_levels() const { return num_levels_; }
+    int64_t nnz() const { return nnz_; }
+
+private:
+    const Ctx &ctx_;
+    int32_t n_, num_levels_ = 0;
+    int64_t nnz_ = 0;
+    bool upper_;
+    int32_t *rp_ = nullptr, *ci_ = nullptr, *order_ = nullptr;   // rows sorted by level
+    double *v_ = nullptr, *inv_diag_ = nullptr;
+    std::vector<int32_t> level_ptr_;   // host: level l = order[level_ptr[l] .. level_ptr[l+1])
+    int32_t *level_ptr_dev_ = nullptr;
+    cudaGraphExec_t graph_ = nullptr;
+    const double *graph_b_ = nullptr;
+    double *graph_x_ = nullptr;
+};
+
+struct RasOptions {
+    double tolerance = 1e-6, local_tol = 1e-12;
+    int32_t local_max_iters = -1, local_solver = 2, non_symmetric = 0, restart_iter = 1,
+            overlap = 2;
+};
+
+// Layout of the peer-visible mailbox of a subdomain (byte offsets from base).
+struct MailboxLayout {
+    int64_t recv_stride = 0;   // bytes between the two receive buffers (epoch parity)
+    int64_t flags_off = 0;     // n_in epoch words (u64)
+    int64_t conv_off = 0;      // P convergence flags (i32)
+    int64_t err_off = 0;       // 1 i32 error word
+    int64_t bytes = 0;
+    static MailboxLayout make(int64_t in_total, int32_t n_in, int32_t P);
+};
+
+// One subdomain.  Vector layout in HBM (compact numbering = g2l - 1 of the
+// reference, source/restricted_schwarz.cpp:155-180, 285-295):
+//   x        [ own (local_size) | overlap (overlap_size) | halo (n_halo) ]
+//   local_*  [ own | overlap ]                              (local_size_x)
+class Ras {
+public:
+    Ras(const Ctx &ctx, Setup &setup, int32_t rank, const double *host_rhs_global,
+        const RasOptions &opt);
+    ~Ras();
+
+    void set_factors(const int32_t *Lrp, const int32_t *Lci, const double *Lv,
+                     const int32_t *perm);
+    void connect(int32_t j_out, void *peer_base, const MailboxLayout &peer_layout,
+                 int32_t peer_recv_offset, int32_t peer_flag_slot, bool same_process);
+
+    // stages of SchwarzBase::run's loop body (source/schwarz_base.cpp:387-452)
+    void exchange_push(int32_t iter);
+    void exchange_unpack(int32_t iter, bool wait_flags);
+    void update_boundary();
+    void local_residual();      // -> *resnorm_dev
+    void local_solve();
+    void restrict_to_x();
+    void wait_push_of(const Ras &nbr);
+    double true_residual_sq();
+    // host-buffer entry points of the plugin path (what SolverRAS::initialize /
+    // run move across PCIe: rhs in, solution out)
+    void upload_rhs(const double *host_rhs_global);          // async H2D via pinned staging
+    void download_solution(double *host_solution_global);    // async D2H of the own block
+    void reset_state();                                      // x, init_guess <- 0; norms unlatched
+    // average duration (ms) of one launch of a hot kernel on this subdomain's
+    // data, CUDA events on the subdomain's stream: 0 SpMV+dot (CG q = A p),
+    // 1 x/r update, 2 p update, 3 residual SpMV+norm, 4 halo push+unpack
+    float kernel_time_ms(int kind, int reps);
+
+    const Ctx &ctx;
+    int32_t rank, P;
+    RasOptions opt;
+    int32_t local_size, local_size_x, overlap_size, n_halo, first_row;
+    std::vector<int32_t> nbr_in, nbr_out, in_count, out_count;
+    MailboxLayout mbox;
+    char *mailbox = nullptr;
+    double *x = nullptr, *local_rhs = nullptr, *local_sol = nullptr, *init_guess = nullptr,
+           *work = nullptr;
+    double *resnorm_dev = nullptr;
+    int32_t *num_converged_dev = nullptr, *conv_sent = nullptr;
+    std::unique_ptr<DeviceCsr> A, I;
+    std::unique_ptr<CgSolver> cg;
+    std::unique_ptr<GmresSolver> gmres;
+    std::unique_ptr<TrsPlan> Ltrs, Utrs;
+    int32_t *fperm = nullptr;
+    cudaEvent_t ev_pushed = nullptr;
+    int32_t last_push_iter = -1;
+    int64_t local_nnz = 0;
+
+    // host-side convergence bookkeeping (source/solve.cpp:796-1005)
+    double resnorm = -1.0, resnorm0 = -1.0, gres = 0.0, gres0 = -1.0;
+    int32_t num_converged = 0, finished_iter = -1;
+    bool finished = false;
+
+    int32_t *conv() const { return (int32_t *)(mailbox + mbox.conv_off); }
+    int32_t *err_word() const { return (int32_t *)(mailbox + mbox.err_off); }
+    void conv_forward(int32_t converged_all_local);
+
+private:
+    int32_t in_total_ = 0, out_total_ = 0;
+    int32_t *in_dst_ = nullptr, *out_src_ = nullptr, *out_off_ = nullptr;
+    std::vector<double *> out_dst_host_[2];
+    std::vector<unsigned long long *> out_flag_host_;
+    std::vector<int32_t *> out_conv_host_;
+    std::vector<char> out_same_process_;
+    double **out_dst_dev_[2] = {nullptr, nullptr};
+    unsigned long long **out_flag_dev_ = nullptr;
+    int32_t **out_conv_dev_ = nullptr;
+    bool any_remote_ = false;
+    int64_t push_epoch_ = 0, unpack_epoch_ = 0;
+    std::vector<int32_t> l2g_local_;     // global ids of [own | overlap]
+    double *pinned_rhs_ = nullptr;
+    void upload_peer_tables();
+    bool peer_tables_dirty_ = true;
+};
+
+struct LoopOptions {
+    int32_t num_subdomains = 1, max_iters = 100;
+    double tolerance = 1e-6;
+    int32_t enable_onesided = 0, enable_global_check = 0, conv_decentralized = 0, iter_offset = 0;
+    Comm *comm = nullptr;
+};
+struct LoopResult {
+    int32_t iters = 0, converged = 0;
+    double global_resnorm = 0.0, global_resnorm0 = -1.0, elapsed_s = 0.0;
+};
+void ras_run(std::vector<Ras *> &subs, const LoopOptions &opt, LoopResult &res,
+             double *resnorm_history);
+
+}  // namespace schwz_b200

@@ -1,0 +1,617 @@
+// sm_100a kernels of the RAS hot path: streaming CSR SpMV with fused
+// reductions, fused CG vector steps with device-resident scalars, halo
+// pack/push + unpack with peer stores and system-scope epoch flags, indexed
+// gather/scatter, permutation, convergence-flag forwarding.
+//
+// Everything here is HBM-bound fp64/int32 work (arithmetic intensity <= 0.17
+// flop/B), so the design rules are: coalesced streaming of rowptr/col/val,
+// >= 8 independent loads in flight per thread, x reused through L1/L2, fixed
+// summation order (bit-reproducible), no host round trips.
+#include <algorithm>
+
+#include "device.hpp"
+
+namespace schwz_b200 {
+
+std::atomic<int64_t> g_launches{0};
+
+// =============================================================================
+// Context
+// =============================================================================
+Ctx::Ctx(int dev) : device(dev)
+{
+    use();
+    SCHWZ_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    partials = alloc<double>(kMaxPartials);
+    tickets = alloc_zero<unsigned int>(16);
+    dev_scalars = alloc_zero<double>(16);
+    SCHWZ_CUDA(cudaMallocHost((void **)&pinned, 16 * sizeof(double)));
+    SCHWZ_CUDA(cudaEventCreate(&ev_start));
+    SCHWZ_CUDA(cudaEventCreate(&ev_stop));
+    SCHWZ_CUDA(cudaStreamSynchronize(stream));
+}
+
+Ctx::~Ctx()
+{
+    cudaSetDevice(device);
+    if (stream) cudaStreamSynchronize(stream);
+    cudaFree(partials);
+    cudaFree(tickets);
+    cudaFree(dev_scalars);
+    if (pinned) cudaFreeHost(pinned);
+    if (ev_start) cudaEventDestroy(ev_start);
+    if (ev_stop) cudaEventDestroy(ev_stop);
+    if (stream) cudaStreamDestroy(stream);
+}
+
+DeviceCsr::~DeviceCsr()
+{
+    if (!ctx) return;
+    ctx->release(rp);
+    ctx->release(ci);
+    ctx->release(v);
+    ctx->release(blk_row);
+}
+
+DeviceCsr *csr_upload(const Ctx &ctx, int32_t nrows, int32_t ncols, const int32_t *rp,
+                      const int32_t *ci, const double *v)
+{
+    auto *A = new DeviceCsr();
+    A->ctx = &ctx;
+    A->nrows = nrows;
+    A->ncols = ncols;
+    A->nnz = nrows > 0 ? rp[nrows] : 0;
+    // Row tiling: greedy, <= kBlock rows and <= kSpmvTile nnz per CTA; a row
+    // longer than the tile gets a CTA of its own (long-row path).
+    std::vector<int32_t> blk;
+    blk.reserve(nrows / kBlock + 2);
+    blk.push_back(0);
+    int32_t r = 0;
+    while (r < nrows) {
+        int32_t r1 = r + 1;   // always take at least one row
+        const int32_t k0 = rp[r];
+        while (r1 < nrows && r1 - r < kBlock && rp[r1 + 1] - k0 <= kSpmvTile) ++r1;
+        blk.push_back(r1);
+        r = r1;
+    }
+    A->nblocks = (int32_t)blk.size() - 1;
+    std::vector<int32_t> rp_fallback(1, 0);
+    A->rp = ctx.upload(nrows > 0 ? rp : rp_fallback.data(), (size_t)nrows + 1);
+    A->ci = ctx.upload(ci, (size_t)A->nnz);
+    A->v = ctx.upload(v, (size_t)A->nnz);
+    A->blk_row = ctx.upload(blk.data(), blk.size());
+    return A;
+}
+
+// =============================================================================
+// Streaming CSR SpMV  (replaces gko::matrix::Csr::apply; the hot kernel of the
+// local solve).  One CTA = one row tile:
+//   phase 1  every thread loads kSpmvUnroll (val, col) pairs of the tile with
+//            fully coalesced 8 B / 4 B loads (all issued before any use), then
+//            gathers x[col] through the read-only path and leaves
+//            (alpha*val)*x in shared memory;
+//   phase 2  thread t sums the products of row t sequentially in stored
+//            column order — the same order as the CPU restatement, so results
+//            are bit-identical and independent of the launch shape.
+// Optional fused epilogue: sum_r y[r]*w[r] or sum_r y[r]^2 via per-CTA
+// partials and a last-CTA ordered final sum.
+// Algorithmic HBM bytes per launch: 12*nnz + 4*(rows+1) + 8*rows (y) +
+// 8*cols (x once) [+ 8*rows if beta != 0] [+ 8*rows for the fused dot operand
+// when it is not x].
+// =============================================================================
+template <int EPI>
+__global__ void __launch_bounds__(kBlock)
+    csr_spmv_stream_kernel(const int32_t *__restrict__ blk_row, const int32_t *__restrict__ rp,
+                           const int32_t *__restrict__ ci, const double *__restrict__ v,
+                           const double *__restrict__ x, double alpha, double beta,
+                           const double *y_in, double *y_out, const double *dot_with,
+                           double *partials, unsigned int *ticket, double *result,
+                           int32_t red_rows, const int32_t *stop)
+{
+    __shared__ double s_prod[kSpmvTile];
+    __shared__ int32_t s_rp[kBlock + 1];
+    __shared__ double s_warp[kBlock / 32];
+
+    if (stop != nullptr && *stop != 0) return;
+
+    const int t = threadIdx.x;
+    const int32_t r0 = blk_row[blockIdx.x];
+    const int32_t nr = blk_row[blockIdx.x + 1] - r0;
+    if (t <= nr) s_rp[t] = rp[r0 + t];
+    __syncthreads();
+    const int32_t k0 = s_rp[0];
+    const int32_t nnz = s_rp[nr] - k0;
+
+    double acc = 0.0;
+    if (nnz <= kSpmvTile) {
+        double vv[kSpmvUnroll];
+        int32_t cc[kSpmvUnroll];
+#pragma unroll
+        for (int i = 0; i < kSpmvUnroll; ++i) {
+            const int k = t + i * kBlock;
+            if (k < nnz) {
+                vv[i] = __ldcs(v + k0 + k);    // streamed once: evict-first
+                cc[i] = __ldcs(ci + k0 + k);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < kSpmvUnroll; ++i) {
+            const int k = t + i * kBlock;
+            if (k < nnz) s_prod[k] = (alpha * vv[i]) * __ldg(x + cc[i]);
+        }
+        __syncthreads();
+        if (t < nr) {
+            const int32_t row = r0 + t;
+            acc = (beta == 0.0) ? 0.0 : beta * y_in[row];
+            const int32_t a = s_rp[t] - k0, b = s_rp[t + 1] - k0;
+            for (int32_t k = a; k < b; ++k) acc += s_prod[k];
+            y_out[row] = acc;
+        }
+    } else {
+        // single long row: CTA-strided products, fixed-shape tree sum
+        double part = 0.0;
+        for (int32_t k = t; k < nnz; k += kBlock)
+            part += (alpha * v[k0 + k]) * __ldg(x + ci[k0 + k]);
+        part = block_sum(part, s_warp);
+        if (t == 0) {
+            acc = ((beta == 0.0) ? 0.0 : beta * y_in[r0]) + part;
+            y_out[r0] = acc;
+        }
+    }
+
+    if (EPI != EPI_NONE) {
+        double c = 0.0;
+        const int32_t row = r0 + t;
+        if (t < nr && row < red_rows) c = (EPI == EPI_DOT) ? acc * dot_with[row] : acc * acc;
+        c = block_sum(c, s_warp);
+        if (t == 0) partials[blockIdx.x] = c;
+        if (last_cta(ticket)) {
+            double s = reduce_partials(partials, gridDim.x, s_warp);
+            if (t == 0) *result = (EPI == EPI_NRM2) ? sqrt(s) : s;
+        }
+    }
+}
+
+void launch_spmv(const Ctx &ctx, const DeviceCsr &A, double alpha, const double *x,
+                 double beta, const double *y_in, double *y_out, SpmvEpilogue epi,
+                 const double *dot_with, double *result, int32_t red_rows,
+                 const int32_t *stop)
+{
+    if (A.nrows == 0) {
+        if (epi != EPI_NONE)
+            SCHWZ_CUDA(cudaMemsetAsync(result, 0, sizeof(double), ctx.stream));
+        return;
+    }
+    SCHWZ_REQUIRE(A.nblocks <= kMaxPartials || epi == EPI_NONE,
+                  "matrix too large for the fused reduction scratch");
+    ctx.use();
+    dim3 grid(A.nblocks), block(kBlock);
+#define SCHWZ_SPMV_CASE(E)                                                                   \
+    csr_spmv_stream_kernel<E><<<grid, block, 0, ctx.stream>>>(                               \
+        A.blk_row, A.rp, A.ci, A.v, x, alpha, beta, y_in, y_out, dot_with, ctx.partials,     \
+        ctx.tickets + 0, result, red_rows, stop)
+    switch (epi) {
+    case EPI_NONE: SCHWZ_SPMV_CASE(EPI_NONE); break;
+    case EPI_DOT: SCHWZ_SPMV_CASE(EPI_DOT); break;
+    case EPI_NRM2SQ: SCHWZ_SPMV_CASE(EPI_NRM2SQ); break;
+    case EPI_NRM2: SCHWZ_SPMV_CASE(EPI_NRM2); break;
+    }
+#undef SCHWZ_SPMV_CASE
+    SCHWZ_CUDA(cudaGetLastError());
+    count_launch();
+}
+
+// =============================================================================
+// BLAS-1
+// =============================================================================
+__global__ void __launch_bounds__(kBlock)
+    dot_kernel(int64_t n, const double *__restrict__ a, const double *__restrict__ b,
+               double *partials, unsigned int *ticket, double *result, int do_sqrt)
+{
+    __shared__ double s_warp[kBlock / 32];
+    double s = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * kBlock)
+        s += a[i] * b[i];
+    s = block_sum(s, s_warp);
+    if (threadIdx.x == 0) partials[blockIdx.x] = s;
+    if (last_cta(ticket)) {
+        double r = reduce_partials(partials, gridDim.x, s_warp);
+        if (threadIdx.x == 0) *result = do_sqrt ? sqrt(r) : r;
+    }
+}
+
+static int vec_grid(int64_t n)
+{
+    int64_t need = (n + kBlock - 1) / kBlock;
+    return (int)std::max<int64_t>(1, std::min<int64_t>(need, kVecGrid));
+}
+
+void launch_dot(const Ctx &ctx, int64_t n, const double *a, const double *b, double *result,
+                bool sqrt_result)
+{
+    ctx.use();
+    dot_kernel<<<vec_grid(n), kBlock, 0, ctx.stream>>>(n, a, b, ctx.partials, ctx.tickets + 1,
+                                                       result, sqrt_result ? 1 : 0);
+    SCHWZ_CUDA(cudaGetLastError());
+    count_launch();
+}
+
+__global__ void __launch_bounds__(kBlock)
+    axpy_kernel(int64_t n, double alpha, const double *__restrict__ x, double *__restrict__ y)
+{
+    for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * kBlock)
+        y[i] += alpha * x[i];
+}
+
+void launch_axpy(const Ctx &ctx, int64_t n, double alpha, const double *x, double *y)
+{
+    if (n <= 0) return;
+    ctx.use();
+    axpy_kernel<<<vec_grid(n), kBlock, 0, ctx.stream>>>(n, alpha, x, y);
+    SCHWZ_CUDA(cudaGetLastError());
+    count_launch();
+}
+
+void launch_copy(const Ctx &ctx, int64_t n, const double *src, double *dst)
+{
+    if (n <= 0) return;
+    ctx.use();
+    SCHWZ_CUDA(cudaMemcpyAsync(dst, src, n * sizeof(double), cudaMemcpyDeviceToDevice, ctx.stream));
+}
+
+// =============================================================================
+// Gather / scatter with the reference's four operations
+// (include/gather.hpp:86-107, include/scatter.hpp:86-108; add 0, copy 1,
+// diff 2, avg 3 — include/collective_common.hpp:37).
+// =============================================================================
+__device__ __forceinline__ double combine(int op, double from, double into)
+{
+    switch (op) {
+    case 0: return from + into;
+    case 2: return from - into;
+    case 3: return (from + into) / 2;
+    default: return from;
+    }
+}
+
+__global__ void __launch_bounds__(kBlock)
+    gather_kernel(int32_t n, const int32_t *__restrict__ idx, const double *__restrict__ from,
+                  double *__restrict__ into, int op)
+{
+    for (int32_t i = blockIdx.x * kBlock + threadIdx.x; i < n; i += gridDim.x * kBlock) {
+        const double f = from[idx[i]];
+        into[i] = (op == 1) ? f : combine(op, f, into[i]);
+    }
+}
+
+__global__ void __launch_bounds__(kBlock)
+    scatter_kernel(int32_t n, const int32_t *__restrict__ idx, const double *__restrict__ from,
+                   double *__restrict__ into, int op)
+{
+    for (int32_t i = blockIdx.x * kBlock + threadIdx.x; i < n; i += gridDim.x * kBlock) {
+        const int32_t j = idx[i];
+        const double f = from[i];
+        into[j] = (op == 1) ? f : combine(op, f, into[j]);
+    }
+}
+
+void launch_gather(const Ctx &ctx, int32_t n, const int32_t *idx, const double *from,
+                   double *into, int op)
+{
+    if (n <= 0) return;
+    ctx.use();
+    gather_kernel<<<vec_grid(n), kBlock, 0, ctx.stream>>>(n, idx, from, into, op);
+    SCHWZ_CUDA(cudaGetLastError());
+    count_launch();
+}
+
+void launch_scatter(const Ctx &ctx, int32_t n, const int32_t *idx, const double *from,
+                    double *into, int op)
+{
+    if (n <= 0) return;
+    ctx.use();
+    scatter_kernel<<<vec_grid(n), kBlock, 0, ctx.stream>>>(n, idx, from, into, op);
+    SCHWZ_CUDA(cudaGetLastError());
+    count_launch();
+}
+
+// gko::matrix::Permutation::apply: row_permute out[i] = in[perm[i]];
+// row_permute|inverse_permute out[perm[i]] = in[i]  (source/solve.cpp:717-720)
+__global__ void __launch_bounds__(kBlock)
+    permute_kernel(int32_t n, const int32_t *__restrict__ perm, int inverse,
+                   const double *__restrict__ in, double *__restrict__ out)
+{
+    for (int32_t i = blockIdx.x * kBlock + threadIdx.x; i < n; i += gridDim.x * kBlock) {
+        if (inverse) out[perm[i]] = in[i];
+        else out[i] = in[perm[i]];
+    }
+}
+
+void launch_permute(const Ctx &ctx, int32_t n, const int32_t *perm, int inverse,
+                    const double *in, double *out)
+{
+    if (n <= 0) return;
+    ctx.use();
+    permute_kernel<<<vec_grid(n), kBlock, 0, ctx.stream>>>(n, perm, inverse, in, out);
+    SCHWZ_CUDA(cudaGetLastError());
+    count_launch();
+}
+
+// =============================================================================
+// CG steps.  Ginkgo Cg ordering:
+//   rho = r.r ; ++iter ; stop? ; p = r + (rho/prev_rho) p ; q = A p ;
+//   beta = p.q ; x += (rho/beta) p ; r -= (rho/beta) q ; swap(prev_rho, rho)
+// All scalars and the stop decision live in CgScalars on the device; every
+// kernel returns at once when stop is set, so the host may enqueue more
+// iterations than are needed and never has to read a scalar back inside the
+// solve.
+// =============================================================================
+__global__ void cg_init_kernel(CgScalars *s, int32_t max_iters, double tol,
+                               const int32_t *outer_stop)
+{
+    // s->rho already holds ||b - A x0||^2 (fused into the residual SpMV)
+    const double r0 = sqrt(s->rho);
+    s->r0 = r0;
+    s->resnorm = r0;
+    s->prev_rho = 1.0;
+    s->beta = 0.0;
+    s->tol = tol;
+    s->iter = 0;
+    s->max_iters = max_iters;
+    // Iteration(max) || ResidualNormReduction(tol): ||r|| < tol * ||r0||
+    int stop = (0 >= max_iters) || (r0 < tol * r0);
+    if (outer_stop != nullptr && *outer_stop != 0) stop = 1;
+    s->stop = stop;
+}
+
+void launch_cg_init(const Ctx &ctx, CgScalars *s, int32_t max_iters, double tol,
+                    const int32_t *outer_stop)
+{
+    ctx.use();
+    cg_init_kernel<<<1, 1, 0, ctx.stream>>>(s, max_iters, tol, outer_stop);
+    SCHWZ_CUDA(cudaGetLastError());
+    count_launch();
+}
+
+// step_1: p = r + (rho/prev_rho) p   (prev_rho == 0 or first iteration: p = r)
+__global__ void __launch_bounds__(kBlock)
+    cg_p_update_kernel(int64_t n, const double *__restrict__ r, double *__restrict__ p,
+                       const CgScalars *__restrict__ s)
+{
+    if (s->stop) return;
+    const bool fresh = (s->iter == 0) || (s->prev_rho == 0.0);
+    const double t = fresh ? 0.0 : s->rho / s->prev_rho;
+    const int64_t n2 = n >> 1;
+    const double2 *r2 = reinterpret_cast<const double2 *>(r);
+    double2 *p2 = reinterpret_cast<double2 *>(p);
+    for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n2;
+         i += (int64_t)gridDim.x * kBlock) {
+        double2 rv = r2[i];
+        if (fresh) {
+            p2[i] = rv;
+        } else {
+            double2 pv = p2[i];
+            pv.x = rv.x + t * pv.x;
+            pv.y = rv.y + t * pv.y;
+            p2[i] = pv;
+        }
+    }
+    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0)
+        p[n - 1] = fresh ? r[n - 1] : r[n - 1] + t * p[n - 1];
+}
+
+void launch_cg_p_update(const Ctx &ctx, int64_t n, const double *r, double *p, const CgScalars *s)
+{
+    ctx.use();
+    cg_p_update_kernel<<<vec_grid((n + 1) / 2), kBlock, 0, ctx.stream>>>(n, r, p, s);
+    SCHWZ_CUDA(cudaGetLastError());
+    count_launch();
+}
+
+// step_2 + next rho + stop test: x += a p ; r -= a q ; rho' = r.r
+__global__ void __launch_bounds__(kBlock)
+    cg_xr_update_kernel(int64_t n, double *__restrict__ x, double *__restrict__ r,
+                        const double *__restrict__ p, const double *__restrict__ q,
+                        CgScalars *s, double *partials, unsigned int *ticket)
+{
+    __shared__ double s_warp[kBlock / 32];
+    if (s->stop) return;
+    const double rho = s->rho, beta = s->beta;
+    const bool skip = (beta == 0.0);
+    const double a = skip ? 0.0 : rho / beta;
+    double acc = 0.0;
+    const int64_t n2 = n >> 1;
+    double2 *x2 = reinterpret_cast<double2 *>(x);
+    double2 *r2 = reinterpret_cast<double2 *>(r);
+    const double2 *p2 = reinterpret_cast<const double2 *>(p);
+    const double2 *q2 = reinterpret_cast<const double2 *>(q);
+    for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n2;
+         i += (int64_t)gridDim.x * kBlock) {
+        double2 rv = r2[i];
+        if (!skip) {
+            double2 xv = x2[i], pv = p2[i], qv = q2[i];
+            xv.x += a * pv.x;
+            xv.y += a * pv.y;
+            rv.x -= a * qv.x;
+            rv.y -= a * qv.y;
+            x2[i] = xv;
+            r2[i] = rv;
+        }
+        acc += rv.x * rv.x + rv.y * rv.y;
+    }
+    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+        double rv = r[n - 1];
+        if (!skip) {
+            x[n - 1] += a * p[n - 1];
+            rv -= a * q[n - 1];
+            r[n - 1] = rv;
+        }
+        acc += rv * rv;
+    }
+    acc = block_sum(acc, s_warp);
+    if (threadIdx.x == 0) partials[blockIdx.x] = acc;
+    if (last_cta(ticket)) {
+        double rho_new = reduce_partials(partials, gridDim.x, s_warp);
+        if (threadIdx.x == 0) {
+            s->prev_rho = rho;
+            s->rho = rho_new;
+            const int it = s->iter + 1;
+            s->iter = it;
+            const double tau = sqrt(rho_new);
+            s->resnorm = tau;
+            if (it >= s->max_iters || tau < s->tol * s->r0) s->stop = 1;
+        }
+    }
+}
+
+void launch_cg_xr_update(const Ctx &ctx, int64_t n, double *x, double *r, const double *p,
+                         const double *q, CgScalars *s)
+{
+    ctx.use();
+    cg_xr_update_kernel<<<vec_grid((n + 1) / 2), kBlock, 0, ctx.stream>>>(
+        n, x, r, p, q, s, ctx.partials, ctx.tickets + 2);
+    SCHWZ_CUDA(cudaGetLastError());
+    count_launch();
+}
+
+// =============================================================================
+// Halo exchange.  One launch packs the values for ALL out-neighbours and
+// stores them straight into the neighbours' receive buffers (peer-mapped over
+// NVLink, or local when the neighbour shares the GPU) — this replaces
+// Gather + MPI_Isend / pack_buffer + MPI_Put (restricted_schwarz.cpp:881-912,
+// comm_helpers.hpp:92-150).  The last CTA then publishes the epoch to each
+// neighbour's flag word with a system-scope release store (≙ MPI_Win_flush).
+// =============================================================================
+constexpr int kMaxSeg = 64;
+
+__global__ void __launch_bounds__(kBlock)
+    halo_pack_push_kernel(int32_t nseg, const int32_t *__restrict__ seg_off, int32_t total,
+                          const int32_t *__restrict__ src_idx, const double *__restrict__ x,
+                          double *const *__restrict__ dst_ptrs,
+                          unsigned long long *const *__restrict__ flag_ptrs,
+                          unsigned long long epoch, unsigned int *ticket, const int32_t *stop)
+{
+    __shared__ int32_t s_off[kMaxSeg + 1];
+    __shared__ double *s_dst[kMaxSeg];
+    if (stop != nullptr && *stop != 0) return;
+    if (threadIdx.x <= nseg) s_off[threadIdx.x] = seg_off[threadIdx.x];
+    if (threadIdx.x < nseg) s_dst[threadIdx.x] = dst_ptrs[threadIdx.x];
+    __syncthreads();
+    for (int32_t e = blockIdx.x * kBlock + threadIdx.x; e < total; e += gridDim.x * kBlock) {
+        int s = 0;
+        while (e >= s_off[s + 1]) ++s;
+        s_dst[s][e - s_off[s]] = x[src_idx[e]];
+    }
+    if (flag_ptrs != nullptr) {
+        __threadfence_system();   // my peer stores are visible system-wide
+        if (last_cta(ticket)) {
+            if (threadIdx.x < nseg) st_release_sys(flag_ptrs[threadIdx.x], epoch);
+        }
+    }
+}
+
+void launch_halo_pack_push(const Ctx &ctx, int32_t nseg, const int32_t *seg_off_dev,
+                           int32_t total, const int32_t *src_idx, const double *x,
+                           double *const *dst_ptrs, unsigned long long *const *flag_ptrs,
+                           unsigned long long epoch, const int32_t *stop)
+{
+    if (nseg <= 0) return;
+    SCHWZ_REQUIRE(nseg <= kMaxSeg, "too many out-neighbours for one push launch");
+    ctx.use();
+    int grid = std::max(1, std::min((total + kBlock - 1) / kBlock, kVecGrid));
+    halo_pack_push_kernel<<<grid, kBlock, 0, ctx.stream>>>(
+        nseg, seg_off_dev, total, src_idx, x, dst_ptrs, flag_ptrs, epoch, ctx.tickets + 3, stop);
+    SCHWZ_CUDA(cudaGetLastError());
+    count_launch();
+}
+
+// Unpack for ALL in-neighbours in one launch (Scatter copy,
+// restricted_schwarz.cpp:955-959 / comm_helpers.hpp:153-177).  With `flags`
+// the kernel first waits until every in-neighbour has published `epoch`
+// (synchronous semantics across processes); without, it scatters whatever the
+// buffer holds (asynchronous semantics).  The wait is bounded so a lost peer
+// cannot hang the GPU; on expiry error_flag is raised.
+__global__ void __launch_bounds__(kBlock)
+    halo_unpack_kernel(int32_t nseg, int32_t total, const int32_t *__restrict__ dst_idx,
+                       const double *recv, double *__restrict__ x,
+                       const unsigned long long *flags, unsigned long long epoch,
+                       int32_t *error_flag)
+{
+    if (flags != nullptr) {
+        if (threadIdx.x < nseg) {
+            long long spins = 0;
+            while (ld_acquire_sys(flags + threadIdx.x) < epoch) {
+                __nanosleep(64);
+                if (++spins > (1ll << 24)) {   // ~1 s
+                    if (error_flag) atomicExch(error_flag, 1);
+                    break;
+                }
+            }
+        }
+        __syncthreads();
+    }
+    const volatile double *rv = recv;   // written by peers: never cache in L1
+    for (int32_t e = blockIdx.x * kBlock + threadIdx.x; e < total; e += gridDim.x * kBlock)
+        x[dst_idx[e]] = rv[e];
+}
+
+void launch_halo_unpack(const Ctx &ctx, int32_t nseg, int32_t total, const int32_t *dst_idx,
+                        const double *recv, double *x, const unsigned long long *flags,
+                        unsigned long long epoch, int32_t *error_flag)
+{
+    if (nseg <= 0 || total <= 0) return;
+    SCHWZ_REQUIRE(nseg <= kBlock, "too many in-neighbours for one unpack launch");
+    ctx.use();
+    int grid = std::max(1, std::min((total + kBlock - 1) / kBlock, kVecGrid));
+    halo_unpack_kernel<<<grid, kBlock, 0, ctx.stream>>>(nseg, total, dst_idx, recv, x, flags,
+                                                        epoch, error_flag);
+    SCHWZ_CUDA(cudaGetLastError());
+    count_launch();
+}
+
+// =============================================================================
+// Decentralised convergence flags, include/conv_tools.hpp:248-274:
+//   if converged_all_local: conv[me] = 1 (sticky)
+//   snapshot = conv ; num = sum(conv)
+//   every out-neighbour gets a remote store of 1 for each flag newly known
+//   conv_sent = snapshot
+// conv lives in the peer-visible mailbox; remote MPI_Put ≙ relaxed system-scope
+// store, MPI_Win_flush ≙ __threadfence_system().
+// =============================================================================
+__global__ void conv_forward_kernel(int32_t P, int32_t me, int32_t converged_all_local,
+                                    int32_t *conv, int32_t *conv_sent, int32_t n_out,
+                                    int32_t *const *peer_conv, int32_t *num_converged)
+{
+    __shared__ int s_num;
+    if (threadIdx.x == 0) {
+        if (converged_all_local == 1) st_relaxed_sys_i32(conv + me, 1);
+        s_num = 0;
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < P; j += blockDim.x) {
+        const int c = ld_relaxed_sys_i32(conv + j);
+        if (c == 1) atomicAdd(&s_num, 1);
+        if (conv_sent[j] == 0 && c == 1) {
+            for (int i = 0; i < n_out; ++i) st_relaxed_sys_i32(peer_conv[i] + j, 1);
+            conv_sent[j] = 1;
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) *num_converged = s_num;
+}
+
+void launch_conv_forward(const Ctx &ctx, int32_t P, int32_t me, int32_t converged_all_local,
+                         int32_t *conv, int32_t *conv_sent, int32_t n_out,
+                         int32_t *const *peer_conv, int32_t *num_converged)
+{
+    ctx.use();
+    conv_forward_kernel<<<1, 128, 0, ctx.stream>>>(P, me, converged_all_local, conv, conv_sent,
+                                                   n_out, peer_conv, num_converged);
+    SCHWZ_CUDA(cudaGetLastError());
+    count_launch();
+}
+
+}  // namespace schwz_b200

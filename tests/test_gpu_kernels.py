@@ -1,0 +1,248 @@
+"""Parity of the sm_100a kernels against the CPU oracle, called through the C
+ABI.  Integer/index work and the row-sequential SpMV are bit-exact; solver
+results are compared at the tolerances stated in each test."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _off(p, nbytes):
+    return C.c_void_p(p.value + nbytes)
+
+
+def _rand_csr(rng, n, m, max_row, long_row=None):
+    lens = rng.integers(0, max_row + 1, size=n)
+    if long_row is not None:
+        lens[long_row[0]] = long_row[1]
+    rp = np.zeros(n + 1, np.int32)
+    rp[1:] = np.cumsum(lens)
+    ci = np.concatenate([np.sort(rng.choice(m, size=l, replace=False)) for l in lens] +
+                        [np.zeros(0, np.int64)]).astype(np.int32)
+    v = rng.standard_normal(rp[-1])
+    return rp, ci, v
+
+
+def test_spmv_bit_exact_laplacian(gpu, sz, orc):
+    rng = np.random.default_rng(0)
+    for mat in (orc.laplacian2d(50), orc.laplacian3d(11)):
+        rp, ci, v = mat
+        n = len(rp) - 1
+        A = sz.Csr(gpu, rp, ci, v)
+        x = rng.standard_normal(n)
+        y0 = rng.standard_normal(n)
+        dx = gpu.to_device(x)
+        for alpha, beta in ((1.0, 0.0), (-1.0, 1.0), (0.37, -2.5)):
+            dy = gpu.to_device(y0)
+            A.spmv(dx, dy, alpha, beta)
+            got = gpu.to_host(dy, n)
+            want = orc.spmv(rp, ci, v, x, alpha, beta, y0)
+            assert np.array_equal(got, want), (alpha, beta)
+            gpu.free(dy)
+        gpu.free(dx)
+        A.close()
+
+
+def test_spmv_bit_exact_ragged_and_edge_cases(gpu, sz, orc):
+    rng = np.random.default_rng(1)
+    cases = [
+        _rand_csr(rng, 1000, 777, 12),                       # ragged, empty rows, rectangular
+        _rand_csr(rng, 300, 5000, 40),                        # rows longer than a warp
+        _rand_csr(rng, 1, 10, 3),                             # one row
+        (np.zeros(6, np.int32), np.zeros(0, np.int32), np.zeros(0)),   # all rows empty
+    ]
+    for rp, ci, v in cases:
+        n = len(rp) - 1
+        m = int(ci.max()) + 1 if len(ci) else 4
+        A = sz.Csr(gpu, rp, ci, v, ncols=m)
+        x = rng.standard_normal(m)
+        y0 = rng.standard_normal(n)
+        dx = gpu.to_device(x)
+        dy = gpu.to_device(y0)
+        A.spmv(dx, dy, -1.0, 1.0)
+        assert np.array_equal(gpu.to_host(dy, n), orc.spmv(rp, ci, v, x, -1.0, 1.0, y0))
+        # beta == 0 must not read y (NaN in y stays out of the result)
+        gpu.h2d(dy, np.full(n, np.nan))
+        A.spmv(dx, dy, 1.0, 0.0)
+        assert np.array_equal(gpu.to_host(dy, n), orc.spmv(rp, ci, v, x, 1.0, 0.0))
+        gpu.free(dx); gpu.free(dy); A.close()
+
+
+def test_spmv_long_row_path(gpu, sz, orc):
+    rng = np.random.default_rng(2)
+    rp, ci, v = _rand_csr(rng, 40, 9000, 6, long_row=(17, 5000))   # > one CTA tile
+    A = sz.Csr(gpu, rp, ci, v, ncols=9000)
+    x = rng.standard_normal(9000)
+    dx = gpu.to_device(x)
+    dy = gpu.zeros(40)
+    A.spmv(dx, dy, 1.0, 0.0)
+    got = gpu.to_host(dy, 40)
+    want = orc.spmv(rp, ci, v, x)
+    mask = np.arange(40) != 17
+    assert np.array_equal(got[mask], want[mask])
+    assert got[17] == pytest.approx(want[17], rel=1e-13)      # tree sum, not sequential
+    gpu.free(dx); gpu.free(dy); A.close()
+
+
+def test_spmv_linearity_large(gpu, sz):
+    # size-independent property at a size the oracle is not asked to run
+    n = 1024
+    S = sz.Setup(("laplacian2d", n), 1)
+    rp, ci, v = S.local_matrix(0)
+    A = sz.Csr(gpu, rp, ci, v)
+    N = n * n
+    rng = np.random.default_rng(3)
+    x1 = rng.standard_normal(N); x2 = rng.standard_normal(N)
+    d1 = gpu.to_device(x1); d2 = gpu.to_device(x2); d3 = gpu.to_device(x1 + 2.0 * x2)
+    y1 = gpu.zeros(N); y2 = gpu.zeros(N); y3 = gpu.zeros(N)
+    A.spmv(d1, y1); A.spmv(d2, y2); A.spmv(d3, y3)
+    h1, h2, h3 = (gpu.to_host(y, N) for y in (y1, y2, y3))
+    np.testing.assert_allclose(h3, h1 + 2.0 * h2, rtol=0, atol=1e-12)
+    # A * ones = boundary indicator of the 5-pt Laplacian: sum = 4n
+    gpu.h2d(d1, np.ones(N)); A.spmv(d1, y1)
+    assert gpu.to_host(y1, N).sum() == 4.0 * n
+    for p in (d1, d2, d3, y1, y2, y3):
+        gpu.free(p)
+    A.close()
+
+
+def test_blas1_and_gather_scatter(gpu, sz):
+    rng = np.random.default_rng(4)
+    for n in (1, 7, 1000, 300001):
+        a = rng.standard_normal(n); b = rng.standard_normal(n)
+        da = gpu.to_device(a); db = gpu.to_device(b)
+        assert gpu.dot(n, da, db) == pytest.approx(float(a @ b), rel=1e-12, abs=1e-12)
+        assert gpu.nrm2(n, da) == pytest.approx(float(np.linalg.norm(a)), rel=1e-13)
+        gpu.axpy(n, -0.75, da, db)
+        assert np.array_equal(gpu.to_host(db, n), b + (-0.75) * a)
+        gpu.free(da); gpu.free(db)
+    n, m = 5000, 20000
+    idx = rng.permutation(m)[:n].astype(np.int32)
+    frm = rng.standard_normal(m); into0 = rng.standard_normal(n)
+    di = gpu.to_device(idx); df = gpu.to_device(frm)
+    # include/gather.hpp:86-107 (OpenMP path semantics)
+    ref = {1: frm[idx], 0: frm[idx] + into0, 2: frm[idx] - into0, 3: (frm[idx] + into0) / 2}
+    for op, want in ref.items():
+        dt = gpu.to_device(into0)
+        gpu.gather(n, di, df, dt, op)
+        assert np.array_equal(gpu.to_host(dt, n), want)
+        gpu.free(dt)
+    # include/scatter.hpp:86-108
+    src = rng.standard_normal(n); tgt0 = rng.standard_normal(m)
+    ds = gpu.to_device(src)
+    for op in (1, 0, 2, 3):
+        want = tgt0.copy()
+        want[idx] = {1: src, 0: src + tgt0[idx], 2: src - tgt0[idx], 3: (src + tgt0[idx]) / 2}[op]
+        dt = gpu.to_device(tgt0)
+        gpu.scatter(n, di, ds, dt, op)
+        assert np.array_equal(gpu.to_host(dt, m), want)
+        gpu.free(dt)
+    # permutation: out[i] = in[perm[i]] / out[perm[i]] = in[i]
+    perm = rng.permutation(n).astype(np.int32)
+    dp = gpu.to_device(perm); dv = gpu.to_device(src); do = gpu.zeros(n)
+    gpu.permute(n, dp, False, dv, do)
+    assert np.array_equal(gpu.to_host(do, n), src[perm])
+    gpu.permute(n, dp, True, dv, do)
+    want = np.zeros(n); want[perm] = src
+    assert np.array_equal(gpu.to_host(do, n), want)
+    for p in (di, df, ds, dp, dv, do):
+        gpu.free(p)
+
+
+def test_cg_matches_oracle(gpu, sz, orc, ani4):
+    rng = np.random.default_rng(5)
+    for (rp, ci, v) in (orc.laplacian2d(40), ani4):
+        n = len(rp) - 1
+        A = sz.Csr(gpu, rp, ci, v)
+        cg = sz.Cg(gpu, A)
+        b = rng.standard_normal(n)
+        x0 = rng.standard_normal(n) * 0.1
+        db = gpu.to_device(b)
+        # (a) fixed budget: exactly K updates, iterates agree to rounding
+        for K in (0, 1, 7, 50):
+            dx = gpu.to_device(x0)
+            cg.solve(db, dx, K, 1e-300)
+            it, rn, r0 = cg.result()
+            xo, ito = orc.cg(rp, ci, v, b, x0, K, 1e-300)
+            assert it == ito == K
+            np.testing.assert_allclose(gpu.to_host(dx, n), xo, rtol=1e-11, atol=1e-13)
+            gpu.free(dx)
+        # (b) to tolerance: same stopping iteration (+-1 at the threshold), same solution
+        dx = gpu.to_device(x0)
+        cg.solve(db, dx, n, 1e-12)
+        it, rn, r0 = cg.result()
+        xo, ito = orc.cg(rp, ci, v, b, x0, n, 1e-12)
+        assert abs(it - ito) <= 1
+        assert rn < 1e-12 * r0
+        got = gpu.to_host(dx, n)
+        assert np.linalg.norm(got - xo) / np.linalg.norm(xo) < 1e-10
+        gpu.free(dx); gpu.free(db); cg.close(); A.close()
+
+
+def test_cg_exact_initial_guess_is_a_no_op(gpu, sz, orc):
+    rp, ci, v = orc.laplacian2d(10)
+    n = 100
+    A = sz.Csr(gpu, rp, ci, v)
+    cg = sz.Cg(gpu, A)
+    db = gpu.zeros(n); dx = gpu.zeros(n)
+    cg.solve(db, dx, 20, 1e-12)      # r0 = 0: 0 < 0 is false -> runs to the cap, x untouched
+    it, rn, r0 = cg.result()
+    assert it == 20 and rn == 0.0
+    assert np.array_equal(gpu.to_host(dx, n), np.zeros(n))
+    gpu.free(db); gpu.free(dx); cg.close(); A.close()
+
+
+def test_gmres_matches_oracle(gpu, sz, orc, ani4):
+    rng = np.random.default_rng(6)
+    rp, ci, v = ani4
+    n = len(rp) - 1
+    A = sz.Csr(gpu, rp, ci, v)
+    b = rng.standard_normal(n)
+    db = gpu.to_device(b)
+    for m, K in ((1, 5), (5, 12), (30, 30), (30, 75)):
+        g = sz.Gmres(gpu, A, m)
+        dx = gpu.zeros(n)
+        g.solve(db, dx, K, 1e-300)
+        it, rn, r0 = g.result()
+        xo, ito = orc.gmres(rp, ci, v, b, np.zeros(n), K, 1e-300, m)
+        assert it == ito == K
+        np.testing.assert_allclose(gpu.to_host(dx, n), xo, rtol=1e-9, atol=1e-11)
+        gpu.free(dx); g.close()
+    g = sz.Gmres(gpu, A, 30)
+    dx = gpu.zeros(n)
+    g.solve(db, dx, 3000, 1e-10)
+    it, rn, r0 = g.result()
+    xo, ito = orc.gmres(rp, ci, v, b, np.zeros(n), 3000, 1e-10, 30)
+    assert abs(it - ito) <= 2
+    got = gpu.to_host(dx, n)
+    assert np.linalg.norm(got - xo) / np.linalg.norm(xo) < 1e-8
+    gpu.free(dx); gpu.free(db); g.close(); A.close()
+
+
+def test_sptrsv_matches_oracle(gpu, sz, orc):
+    rng = np.random.default_rng(7)
+    rp, ci, v = orc.laplacian2d(30)
+    n = len(rp) - 1
+    for perm in (None, sz.nd_ordering(rp, ci)):
+        Lrp, Lci, Lv = sz.host_cholesky(rp, ci, v, perm)
+        import scipy.sparse as sp
+        U = sp.csr_matrix((Lv, Lci, Lrp), shape=(n, n)).T.tocsr(); U.sort_indices()
+        Urp, Uci, Uv = U.indptr.astype(np.int32), U.indices.astype(np.int32), U.data
+        b = rng.standard_normal(n)
+        db = gpu.to_device(b); dy = gpu.zeros(n); dz = gpu.zeros(n)
+        tl = sz.Trs(gpu, Lrp, Lci, Lv, upper=False)
+        tu = sz.Trs(gpu, Urp, Uci, Uv, upper=True)
+        assert 1 <= tl.levels() <= n and tl.levels() == tu.levels()
+        tl.solve(db, dy); tu.solve(dy, dz)
+        yo = orc.trs(Lrp, Lci, Lv, b, upper=False)
+        zo = orc.trs(Urp, Uci, Uv, yo, upper=True)
+        np.testing.assert_allclose(gpu.to_host(dy, n), yo, rtol=1e-12, atol=1e-14)
+        np.testing.assert_allclose(gpu.to_host(dz, n), zo, rtol=1e-11, atol=1e-13)
+        # replay of the captured level graph gives the same answer
+        tl.solve(db, dy)
+        np.testing.assert_allclose(gpu.to_host(dy, n), yo, rtol=1e-12, atol=1e-14)
+        for p in (db, dy, dz):
+            gpu.free(p)
+        tl.close(); tu.close()
