@@ -59,6 +59,8 @@ int schwz_b200_device_count(int *count)
 int schwz_b200_ctx_create(int device, schwz_ctx **out)
 {
     ABI_BEGIN
+    const char *e = std::getenv("SCHWZ_B200_SIMPLE_SPMV");
+    g_force_simple_spmv = e && e[0] == '1';
     *out = new schwz_ctx(device);
     ABI_END
 }

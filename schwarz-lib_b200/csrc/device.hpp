@@ -70,9 +70,11 @@ struct DeviceCsr {
     double *v = nullptr;
     int32_t nblocks = 0;
     int32_t *blk_row = nullptr;
+    bool has_long_row = false;
     ~DeviceCsr();
 };
 
+extern bool g_force_simple_spmv;
 DeviceCsr *csr_upload(const Ctx &ctx, int32_t nrows, int32_t ncols, const int32_t *rp,
                       const int32_t *ci, const double *v);
 

@@ -14,6 +14,7 @@
 namespace schwz_b200 {
 
 std::atomic<int64_t> g_launches{0};
+bool g_force_simple_spmv = false;   // SCHWZ_B200_SIMPLE_SPMV=1: one-shot kernel (A/B measurements)
 
 // =============================================================================
 // Context
@@ -75,10 +76,22 @@ DeviceCsr *csr_upload(const Ctx &ctx, int32_t nrows, int32_t ncols, const int32_
         r = r1;
     }
     A->nblocks = (int32_t)blk.size() - 1;
+    A->has_long_row = false;
+    for (int32_t b = 0; b < A->nblocks; ++b)
+        if (rp[blk[b + 1]] - rp[blk[b]] > kSpmvTile) A->has_long_row = true;
+    // The pipelined kernel copies 16-byte aligned supersets of each tile, so
+    // every array is padded by 8 elements past its end.
+    auto upload_padded = [&](auto *host, size_t n, auto zero) {
+        using T = decltype(zero);
+        T *d = ctx.alloc_zero<T>(n + 8);
+        if (n) SCHWZ_CUDA(cudaMemcpyAsync(d, host, n * sizeof(T), cudaMemcpyHostToDevice, ctx.stream));
+        SCHWZ_CUDA(cudaStreamSynchronize(ctx.stream));
+        return d;
+    };
     std::vector<int32_t> rp_fallback(1, 0);
-    A->rp = ctx.upload(nrows > 0 ? rp : rp_fallback.data(), (size_t)nrows + 1);
-    A->ci = ctx.upload(ci, (size_t)A->nnz);
-    A->v = ctx.upload(v, (size_t)A->nnz);
+    A->rp = upload_padded(nrows > 0 ? rp : rp_fallback.data(), (size_t)nrows + 1, int32_t(0));
+    A->ci = upload_padded(ci, (size_t)A->nnz, int32_t(0));
+    A->v = upload_padded(v, (size_t)A->nnz, double(0));
     A->blk_row = ctx.upload(blk.data(), blk.size());
     return A;
 }
@@ -117,7 +130,7 @@ __global__ void __launch_bounds__(kBlock)
     const int t = threadIdx.x;
     const int32_t r0 = blk_row[blockIdx.x];
     const int32_t nr = blk_row[blockIdx.x + 1] - r0;
-    if (t <= nr) s_rp[t] = rp[r0 + t];
+    for (int i = t; i <= nr; i += kBlock) s_rp[i] = rp[r0 + i];   // nr + 1 <= kBlock + 1 entries
     __syncthreads();
     const int32_t k0 = s_rp[0];
     const int32_t nnz = s_rp[nr] - k0;
@@ -172,6 +185,225 @@ __global__ void __launch_bounds__(kBlock)
     }
 }
 
+// =============================================================================
+// Persistent, warp-specialised, TMA-pipelined variant of the streaming SpMV —
+// the production path.  Grid = kSpmvCtasPerSM CTAs per SM; each CTA walks the
+// row tiles b, b + grid, ...  One producer warp keeps kSpmvStages tiles in
+// flight: for every tile a single lane issues three cp.async.bulk copies
+// (val, col, rowptr; 16-byte aligned supersets of the tile's ranges, L2
+// evict-first) that complete on the stage's "full" mbarrier.  Eight consumer
+// warps wait on that barrier, gather x through the read-only path, leave
+// (alpha*val)*x in shared memory, synchronise among themselves on a named
+// barrier, sum each row sequentially in stored order (bit-identical to the CPU
+// restatement), store y and release the stage on its "empty" mbarrier.  The
+// HBM stream of tile i+2 therefore overlaps the gather and the row sums of
+// tile i, which is what the one-shot kernel above cannot do.
+// =============================================================================
+constexpr int kSpmvStages = 3;
+constexpr int kSpmvChunk = 8;     // non-zeros of a row gathered per round
+constexpr int kSpmvCtasPerSM = 2;
+constexpr int kSpmvThreads = kBlock + 32;   // 8 consumer warps + 1 producer warp
+
+struct __align__(16) SpmvStage {
+    double val[kSpmvTile + 8];
+    int32_t col[kSpmvTile + 8];
+    int32_t rp[kBlock + 8];
+};
+struct __align__(16) SpmvSmem {
+    SpmvStage st[kSpmvStages];
+    double warp_buf[kBlock / 32];
+    unsigned long long full[kSpmvStages], empty[kSpmvStages];
+    int last;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
+{
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(void *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(void *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(void *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(void *bar, uint32_t parity)
+{
+    const uint32_t addr = smem_u32(bar);
+    uint32_t ok = 0;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(addr), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+// TMA 1-D bulk copy global -> shared, completion counted on an mbarrier
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, void *bar,
+                                         unsigned long long policy)
+{
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint "
+        "[%0], [%1], %2, [%3], %4;" ::"r"(smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+        : "memory");
+}
+__device__ __forceinline__ void consumer_sync()
+{
+    asm volatile("bar.sync 1, %0;" ::"n"(kBlock) : "memory");
+}
+
+template <int EPI>
+__global__ void __launch_bounds__(kSpmvThreads, kSpmvCtasPerSM)
+    csr_spmv_tma_kernel(int32_t ntiles, const int32_t *__restrict__ blk_row,
+                        const int32_t *__restrict__ rp, const int32_t *__restrict__ ci,
+                        const double *__restrict__ v, const double *__restrict__ x, double alpha,
+                        double beta, const double *y_in, double *y_out, const double *dot_with,
+                        double *partials, unsigned int *ticket, double *result, int32_t red_rows,
+                        const int32_t *stop)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    SpmvSmem &S = *reinterpret_cast<SpmvSmem *>(smem_raw);
+    if (stop != nullptr && *stop != 0) return;
+
+    const int t = threadIdx.x;
+    if (t == 0) {
+        for (int s = 0; s < kSpmvStages; ++s) {
+            mbar_init(&S.full[s], 1);
+            mbar_init(&S.empty[s], kBlock / 32);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (t >= kBlock) {
+        // ------------------------------ producer warp ------------------------
+        if (t == kBlock) {
+            unsigned long long policy;
+            asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+            int it = 0;
+            for (int32_t b = blockIdx.x; b < ntiles; b += gridDim.x, ++it) {
+                const int s = it % kSpmvStages;
+                mbar_wait(&S.empty[s], ((it / kSpmvStages) & 1) ^ 1);
+                const int32_t r0 = blk_row[b], r1 = blk_row[b + 1];
+                const int32_t k0 = rp[r0], k1 = rp[r1];
+                const int32_t k0a = k0 & ~3, k1a = (k1 + 3) & ~3;       // 4-element granules
+                const int32_t r0a = r0 & ~3, r1a = (r1 + 1 + 3) & ~3;
+                const uint32_t nv = (uint32_t)(k1a - k0a), nr = (uint32_t)(r1a - r0a);
+                mbar_expect_tx(&S.full[s], nv * 12u + nr * 4u);
+                if (nv) {
+                    bulk_g2s(S.st[s].val, v + k0a, nv * 8u, &S.full[s], policy);
+                    bulk_g2s(S.st[s].col, ci + k0a, nv * 4u, &S.full[s], policy);
+                }
+                bulk_g2s(S.st[s].rp, rp + r0a, nr * 4u, &S.full[s], policy);
+            }
+        }
+        return;
+    }
+
+    // -------------------------------- consumers ------------------------------
+    // Thread t owns row r0 + t of the tile and walks it in stored order straight
+    // out of the staged tile: per non-zero one LDS.64 (val), one LDS.32 (col)
+    // and one x gather.  Neighbouring threads own neighbouring rows, so for
+    // stencil-like matrices the j-th gathers of a warp fall on consecutive
+    // addresses (coalesced) and the staged reads are bank-conflict free
+    // (stride = row length).  No barrier between warps: each warp releases the
+    // stage as soon as its 32 rows are done.
+    double red = 0.0;
+    int it = 0;
+    for (int32_t b = blockIdx.x; b < ntiles; b += gridDim.x, ++it) {
+        const int s = it % kSpmvStages;
+        const int32_t r0 = blk_row[b];
+        const int32_t nr = blk_row[b + 1] - r0;
+        mbar_wait(&S.full[s], (it / kSpmvStages) & 1);
+        const SpmvStage &T = S.st[s];
+        const int32_t *srp = T.rp + (r0 & 3);
+        if (t < nr) {
+            const int32_t row = r0 + t;
+            const int32_t base = (srp[0] & ~3);          // first staged element
+            const int32_t e = srp[t + 1] - base;
+            double acc = (beta == 0.0) ? 0.0 : beta * y_in[row];
+            for (int32_t k = srp[t] - base; k < e; k += kSpmvChunk) {
+                double xv[kSpmvChunk], vv[kSpmvChunk];
+#pragma unroll
+                for (int i = 0; i < kSpmvChunk; ++i)
+                    if (k + i < e) {
+                        xv[i] = __ldg(x + T.col[k + i]);
+                        vv[i] = T.val[k + i];
+                    }
+#pragma unroll
+                for (int i = 0; i < kSpmvChunk; ++i)
+                    if (k + i < e) acc += (alpha * vv[i]) * xv[i];
+            }
+            y_out[row] = acc;
+            if (EPI != EPI_NONE && row < red_rows)
+                red += (EPI == EPI_DOT) ? acc * dot_with[row] : acc * acc;
+        }
+        __syncwarp();
+        if ((t & 31) == 0) mbar_arrive(&S.empty[s]);
+    }
+
+    if (EPI != EPI_NONE) {
+        // CTA-wide sum over the 8 consumer warps, then last-CTA ordered final sum
+        red = warp_sum(red);
+        if ((t & 31) == 0) S.warp_buf[t >> 5] = red;
+        consumer_sync();
+        if (t < 32) {
+            double c = t < (kBlock / 32) ? S.warp_buf[t] : 0.0;
+            c = warp_sum(c);
+            if (t == 0) {
+                partials[blockIdx.x] = c;
+                __threadfence();
+                const unsigned int tk = atomicAdd(ticket, 1u);
+                S.last = (tk == gridDim.x - 1);
+                if (S.last) *ticket = 0u;
+            }
+        }
+        consumer_sync();
+        if (S.last) {
+            __threadfence();
+            double sacc = 0.0;
+            for (int i = t; i < (int)gridDim.x; i += kBlock) sacc += __ldcg(partials + i);
+            sacc = warp_sum(sacc);
+            if ((t & 31) == 0) S.warp_buf[t >> 5] = sacc;
+            consumer_sync();
+            if (t < 32) {
+                double c = t < (kBlock / 32) ? S.warp_buf[t] : 0.0;
+                c = warp_sum(c);
+                if (t == 0) *result = (EPI == EPI_NRM2) ? sqrt(c) : c;
+            }
+        }
+    }
+}
+
+template <int EPI>
+static void launch_spmv_tma(const Ctx &ctx, const DeviceCsr &A, double alpha, const double *x,
+                            double beta, const double *y_in, double *y_out, const double *dot_with,
+                            double *result, int32_t red_rows, const int32_t *stop)
+{
+    static bool configured[64] = {};
+    if (!configured[ctx.device]) {
+        SCHWZ_CUDA(cudaFuncSetAttribute(csr_spmv_tma_kernel<EPI>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)sizeof(SpmvSmem)));
+        configured[ctx.device] = true;
+    }
+    const int grid = std::min<int>(A.nblocks, kNumSMs * kSpmvCtasPerSM);
+    csr_spmv_tma_kernel<EPI><<<grid, kSpmvThreads, sizeof(SpmvSmem), ctx.stream>>>(
+        A.nblocks, A.blk_row, A.rp, A.ci, A.v, x, alpha, beta, y_in, y_out, dot_with, ctx.partials,
+        ctx.tickets + 0, result, red_rows, stop);
+}
+
 void launch_spmv(const Ctx &ctx, const DeviceCsr &A, double alpha, const double *x,
                  double beta, const double *y_in, double *y_out, SpmvEpilogue epi,
                  const double *dot_with, double *result, int32_t red_rows,
@@ -185,6 +417,17 @@ void launch_spmv(const Ctx &ctx, const DeviceCsr &A, double alpha, const double 
     SCHWZ_REQUIRE(A.nblocks <= kMaxPartials || epi == EPI_NONE,
                   "matrix too large for the fused reduction scratch");
     ctx.use();
+    if (!A.has_long_row && !g_force_simple_spmv) {
+        switch (epi) {
+        case EPI_NONE: launch_spmv_tma<EPI_NONE>(ctx, A, alpha, x, beta, y_in, y_out, dot_with, result, red_rows, stop); break;
+        case EPI_DOT: launch_spmv_tma<EPI_DOT>(ctx, A, alpha, x, beta, y_in, y_out, dot_with, result, red_rows, stop); break;
+        case EPI_NRM2SQ: launch_spmv_tma<EPI_NRM2SQ>(ctx, A, alpha, x, beta, y_in, y_out, dot_with, result, red_rows, stop); break;
+        case EPI_NRM2: launch_spmv_tma<EPI_NRM2>(ctx, A, alpha, x, beta, y_in, y_out, dot_with, result, red_rows, stop); break;
+        }
+        SCHWZ_CUDA(cudaGetLastError());
+        count_launch();
+        return;
+    }
     dim3 grid(A.nblocks), block(kBlock);
 #define SCHWZ_SPMV_CASE(E)                                                                   \
     csr_spmv_stream_kernel<E><<<grid, block, 0, ctx.stream>>>(                               \

