@@ -193,6 +193,8 @@ def main():
         run_reference(args)
         return
 
+    # keep stdout to the one JSON line: NCCL's banner goes to stderr
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     import torch
     import torch.distributed as dist
     import schwz_b200 as S
@@ -233,17 +235,14 @@ def main():
         info = {}
         for d in allinfo:
             info.update(d)
-        for s in subs:
-            _, nout = s.neighbors()
-            pd, _ = setup.displacements(s.rank)
-            for j, q in enumerate(nout.tolist()):
-                if q in my:
-                    continue
-                handle, lay, q_in = info[q]
-                if q not in imported:
-                    imported[q] = s.ctx.ipc_import(handle)
-                s.connect(j, imported[q], S.MailboxLayout.from_tuple(lay), int(pd[q]),
-                          q_in.index(s.rank), same_process=False)
+        by_rank = {s.rank: s for s in subs}
+        plan = S.remote_connection_plan(setup, my, {q: v[2] for q, v in info.items()})
+        for r, j, q, recv_off, slot in plan:
+            handle, lay, _ = info[q]
+            if q not in imported:
+                imported[q] = by_rank[r].ctx.ipc_import(handle)
+            by_rank[r].connect(j, imported[q], S.MailboxLayout.from_tuple(lay), recv_off, slot,
+                               same_process=False)
         uid = [S.Comm.unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         comm = S.Comm(ctxs[0], uid[0], world, rank)

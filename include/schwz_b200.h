@@ -228,6 +228,10 @@ typedef struct {
     int64_t bytes;
 } schwz_mailbox_layout;
 int schwz_b200_ras_mailbox(schwz_ras *r, void **dev_base, schwz_mailbox_layout *layout);
+/* host only: the layout implied by the index-set sizes (in_total = sum of the
+ * in-list lengths, n_in = num_neighbors_in) */
+int schwz_b200_mailbox_layout(int64_t in_total, int32_t n_in, int32_t P,
+                              schwz_mailbox_layout *layout);
 /* sizes a peer needs: out[0] = num_neighbors_in, out[1] = num_neighbors_out,
  * out[2] = local_size, out[3] = local_size_x, out[4] = n_halo, out[5] = nnz_local */
 int schwz_b200_ras_info(schwz_ras *r, int64_t *out);

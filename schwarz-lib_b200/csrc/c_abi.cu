@@ -61,6 +61,8 @@ int schwz_b200_ctx_create(int device, schwz_ctx **out)
     ABI_BEGIN
     const char *e = std::getenv("SCHWZ_B200_SIMPLE_SPMV");
     g_force_simple_spmv = e && e[0] == '1';
+    const char *vr = std::getenv("SCHWZ_B200_SPMV_VARIANT");
+    if (vr) g_spmv_variant = std::atoi(vr);
     *out = new schwz_ctx(device);
     ABI_END
 }
@@ -588,6 +590,17 @@ int schwz_b200_ras_mailbox(schwz_ras *r, void **base, schwz_mailbox_layout *l)
     l->conv_off = r->impl->mbox.conv_off;
     l->err_off = r->impl->mbox.err_off;
     l->bytes = r->impl->mbox.bytes;
+    ABI_END
+}
+int schwz_b200_mailbox_layout(int64_t in_total, int32_t n_in, int32_t P, schwz_mailbox_layout *l)
+{
+    ABI_BEGIN
+    MailboxLayout m = MailboxLayout::make(in_total, n_in, P);
+    l->recv_stride = m.recv_stride;
+    l->flags_off = m.flags_off;
+    l->conv_off = m.conv_off;
+    l->err_off = m.err_off;
+    l->bytes = m.bytes;
     ABI_END
 }
 int schwz_b200_ras_info(schwz_ras *r, int64_t *out)

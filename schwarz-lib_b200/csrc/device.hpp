@@ -71,10 +71,12 @@ struct DeviceCsr {
     int32_t nblocks = 0;
     int32_t *blk_row = nullptr;
     bool has_long_row = false;
+    int32_t rows_per_tile = kBlock;
     ~DeviceCsr();
 };
 
 extern bool g_force_simple_spmv;
+extern int g_spmv_variant;
 DeviceCsr *csr_upload(const Ctx &ctx, int32_t nrows, int32_t ncols, const int32_t *rp,
                       const int32_t *ci, const double *v);
 

@@ -15,6 +15,7 @@ namespace schwz_b200 {
 
 std::atomic<int64_t> g_launches{0};
 bool g_force_simple_spmv = false;   // SCHWZ_B200_SIMPLE_SPMV=1: one-shot kernel (A/B measurements)
+int g_spmv_variant = 1;             // SCHWZ_B200_SPMV_VARIANT: launch shape of the pipelined kernel
 
 // =============================================================================
 // Context
@@ -64,21 +65,38 @@ DeviceCsr *csr_upload(const Ctx &ctx, int32_t nrows, int32_t ncols, const int32_
     A->nnz = nrows > 0 ? rp[nrows] : 0;
     // Row tiling: greedy, <= kBlock rows and <= kSpmvTile nnz per CTA; a row
     // longer than the tile gets a CTA of its own (long-row path).
+    const int rpt = (g_spmv_variant >= 3) ? 2 : 1;
+    A->rows_per_tile = kBlock * rpt;
+    const int32_t tile_rows = A->rows_per_tile, tile_nnz = kSpmvTile * rpt;
     std::vector<int32_t> blk;
-    blk.reserve(nrows / kBlock + 2);
+    blk.reserve(nrows / tile_rows + 2);
     blk.push_back(0);
     int32_t r = 0;
     while (r < nrows) {
         int32_t r1 = r + 1;   // always take at least one row
         const int32_t k0 = rp[r];
-        while (r1 < nrows && r1 - r < kBlock && rp[r1 + 1] - k0 <= kSpmvTile) ++r1;
+        while (r1 < nrows && r1 - r < tile_rows && rp[r1 + 1] - k0 <= tile_nnz) ++r1;
         blk.push_back(r1);
         r = r1;
     }
     A->nblocks = (int32_t)blk.size() - 1;
     A->has_long_row = false;
     for (int32_t b = 0; b < A->nblocks; ++b)
-        if (rp[blk[b + 1]] - rp[blk[b]] > kSpmvTile) A->has_long_row = true;
+        if (rp[blk[b + 1]] - rp[blk[b]] > tile_nnz) A->has_long_row = true;
+    if (A->has_long_row && rpt != 1) {
+        // the one-shot fallback kernel works on kBlock-row tiles: retile
+        A->rows_per_tile = kBlock;
+        blk.assign(1, 0);
+        r = 0;
+        while (r < nrows) {
+            int32_t r1 = r + 1;
+            const int32_t k0 = rp[r];
+            while (r1 < nrows && r1 - r < kBlock && rp[r1 + 1] - k0 <= kSpmvTile) ++r1;
+            blk.push_back(r1);
+            r = r1;
+        }
+        A->nblocks = (int32_t)blk.size() - 1;
+    }
     // The pipelined kernel copies 16-byte aligned supersets of each tile, so
     // every array is padded by 8 elements past its end.
     auto upload_padded = [&](auto *host, size_t n, auto zero) {
@@ -199,20 +217,23 @@ __global__ void __launch_bounds__(kBlock)
 // HBM stream of tile i+2 therefore overlaps the gather and the row sums of
 // tile i, which is what the one-shot kernel above cannot do.
 // =============================================================================
-constexpr int kSpmvStages = 3;
-constexpr int kSpmvChunk = 8;     // non-zeros of a row gathered per round
-constexpr int kSpmvCtasPerSM = 2;
+// Launch shapes of the pipelined kernel: RPT rows per consumer thread (a tile is
+// kBlock*RPT rows), STAGES tiles in flight per CTA, CTAS resident CTAs per SM.
+// DeviceCsr::rows_per_tile fixes RPT at upload time.
+constexpr int kSpmvChunk = 6;     // non-zeros of a row gathered per round
 constexpr int kSpmvThreads = kBlock + 32;   // 8 consumer warps + 1 producer warp
 
+template <int RPT>
 struct __align__(16) SpmvStage {
-    double val[kSpmvTile + 8];
-    int32_t col[kSpmvTile + 8];
-    int32_t rp[kBlock + 8];
+    double val[kSpmvTile * RPT + 8];
+    int32_t col[kSpmvTile * RPT + 8];
+    int32_t rp[kBlock * RPT + 8];
 };
+template <int RPT, int STAGES>
 struct __align__(16) SpmvSmem {
-    SpmvStage st[kSpmvStages];
+    SpmvStage<RPT> st[STAGES];
     double warp_buf[kBlock / 32];
-    unsigned long long full[kSpmvStages], empty[kSpmvStages];
+    unsigned long long full[STAGES], empty[STAGES];
     int last;
 };
 
@@ -263,8 +284,8 @@ __device__ __forceinline__ void consumer_sync()
     asm volatile("bar.sync 1, %0;" ::"n"(kBlock) : "memory");
 }
 
-template <int EPI>
-__global__ void __launch_bounds__(kSpmvThreads, kSpmvCtasPerSM)
+template <int EPI, int RPT, int STAGES, int CTAS>
+__global__ void __launch_bounds__(kSpmvThreads, CTAS)
     csr_spmv_tma_kernel(int32_t ntiles, const int32_t *__restrict__ blk_row,
                         const int32_t *__restrict__ rp, const int32_t *__restrict__ ci,
                         const double *__restrict__ v, const double *__restrict__ x, double alpha,
@@ -273,12 +294,13 @@ __global__ void __launch_bounds__(kSpmvThreads, kSpmvCtasPerSM)
                         const int32_t *stop)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    SpmvSmem &S = *reinterpret_cast<SpmvSmem *>(smem_raw);
+    using Smem = SpmvSmem<RPT, STAGES>;
+    Smem &S = *reinterpret_cast<Smem *>(smem_raw);
     if (stop != nullptr && *stop != 0) return;
 
     const int t = threadIdx.x;
     if (t == 0) {
-        for (int s = 0; s < kSpmvStages; ++s) {
+        for (int s = 0; s < STAGES; ++s) {
             mbar_init(&S.full[s], 1);
             mbar_init(&S.empty[s], kBlock / 32);
         }
@@ -293,13 +315,13 @@ __global__ void __launch_bounds__(kSpmvThreads, kSpmvCtasPerSM)
             asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
             int it = 0;
             for (int32_t b = blockIdx.x; b < ntiles; b += gridDim.x, ++it) {
-                const int s = it % kSpmvStages;
-                mbar_wait(&S.empty[s], ((it / kSpmvStages) & 1) ^ 1);
+                const int s = it % STAGES;
                 const int32_t r0 = blk_row[b], r1 = blk_row[b + 1];
                 const int32_t k0 = rp[r0], k1 = rp[r1];
                 const int32_t k0a = k0 & ~3, k1a = (k1 + 3) & ~3;       // 4-element granules
                 const int32_t r0a = r0 & ~3, r1a = (r1 + 1 + 3) & ~3;
                 const uint32_t nv = (uint32_t)(k1a - k0a), nr = (uint32_t)(r1a - r0a);
+                mbar_wait(&S.empty[s], ((it / STAGES) & 1) ^ 1);
                 mbar_expect_tx(&S.full[s], nv * 12u + nr * 4u);
                 if (nv) {
                     bulk_g2s(S.st[s].val, v + k0a, nv * 8u, &S.full[s], policy);
@@ -312,42 +334,69 @@ __global__ void __launch_bounds__(kSpmvThreads, kSpmvCtasPerSM)
     }
 
     // -------------------------------- consumers ------------------------------
-    // Thread t owns row r0 + t of the tile and walks it in stored order straight
-    // out of the staged tile: per non-zero one LDS.64 (val), one LDS.32 (col)
-    // and one x gather.  Neighbouring threads own neighbouring rows, so for
-    // stencil-like matrices the j-th gathers of a warp fall on consecutive
-    // addresses (coalesced) and the staged reads are bank-conflict free
-    // (stride = row length).  No barrier between warps: each warp releases the
-    // stage as soon as its 32 rows are done.
+    // Thread t owns rows r0 + t + j*kBlock (j < RPT) of the tile and walks them
+    // in stored order straight out of the staged tile: per non-zero one LDS.64
+    // (val), one LDS.32 (col) and one x gather.  Neighbouring threads own
+    // neighbouring rows, so for stencil-like matrices the i-th gathers of a
+    // warp fall on consecutive addresses (coalesced) and the staged reads are
+    // bank-conflict free (stride = row length).  All RPT*kSpmvChunk gathers of
+    // a round are issued before the first use.  No barrier between warps: each
+    // warp releases the stage as soon as its rows are done.
     double red = 0.0;
     int it = 0;
     for (int32_t b = blockIdx.x; b < ntiles; b += gridDim.x, ++it) {
-        const int s = it % kSpmvStages;
+        const int s = it % STAGES;
         const int32_t r0 = blk_row[b];
         const int32_t nr = blk_row[b + 1] - r0;
-        mbar_wait(&S.full[s], (it / kSpmvStages) & 1);
-        const SpmvStage &T = S.st[s];
+        mbar_wait(&S.full[s], (it / STAGES) & 1);
+        const SpmvStage<RPT> &T = S.st[s];
         const int32_t *srp = T.rp + (r0 & 3);
-        if (t < nr) {
-            const int32_t row = r0 + t;
-            const int32_t base = (srp[0] & ~3);          // first staged element
-            const int32_t e = srp[t + 1] - base;
-            double acc = (beta == 0.0) ? 0.0 : beta * y_in[row];
-            for (int32_t k = srp[t] - base; k < e; k += kSpmvChunk) {
-                double xv[kSpmvChunk], vv[kSpmvChunk];
+        const int32_t base = (srp[0] & ~3);   // first staged element
+        int32_t k[RPT], e[RPT];
+        double acc[RPT];
+        bool more = false;
 #pragma unroll
-                for (int i = 0; i < kSpmvChunk; ++i)
-                    if (k + i < e) {
-                        xv[i] = __ldg(x + T.col[k + i]);
-                        vv[i] = T.val[k + i];
-                    }
-#pragma unroll
-                for (int i = 0; i < kSpmvChunk; ++i)
-                    if (k + i < e) acc += (alpha * vv[i]) * xv[i];
+        for (int j = 0; j < RPT; ++j) {
+            const int32_t lr = t + j * kBlock;
+            if (lr < nr) {
+                k[j] = srp[lr] - base;
+                e[j] = srp[lr + 1] - base;
+                acc[j] = (beta == 0.0) ? 0.0 : beta * y_in[r0 + lr];
+            } else {
+                k[j] = e[j] = 0;
+                acc[j] = 0.0;
             }
-            y_out[row] = acc;
-            if (EPI != EPI_NONE && row < red_rows)
-                red += (EPI == EPI_DOT) ? acc * dot_with[row] : acc * acc;
+            more |= k[j] < e[j];
+        }
+        while (more) {
+            double xv[RPT][kSpmvChunk], vv[RPT][kSpmvChunk];
+#pragma unroll
+            for (int j = 0; j < RPT; ++j)
+#pragma unroll
+                for (int i = 0; i < kSpmvChunk; ++i)
+                    if (k[j] + i < e[j]) {
+                        xv[j][i] = __ldg(x + T.col[k[j] + i]);
+                        vv[j][i] = T.val[k[j] + i];
+                    }
+            more = false;
+#pragma unroll
+            for (int j = 0; j < RPT; ++j) {
+#pragma unroll
+                for (int i = 0; i < kSpmvChunk; ++i)
+                    if (k[j] + i < e[j]) acc[j] += (alpha * vv[j][i]) * xv[j][i];
+                k[j] += kSpmvChunk;
+                more |= k[j] < e[j];
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < RPT; ++j) {
+            const int32_t lr = t + j * kBlock;
+            if (lr < nr) {
+                const int32_t row = r0 + lr;
+                y_out[row] = acc[j];
+                if (EPI != EPI_NONE && row < red_rows)
+                    red += (EPI == EPI_DOT) ? acc[j] * dot_with[row] : acc[j] * acc[j];
+            }
         }
         __syncwarp();
         if ((t & 31) == 0) mbar_arrive(&S.empty[s]);
@@ -386,22 +435,48 @@ __global__ void __launch_bounds__(kSpmvThreads, kSpmvCtasPerSM)
     }
 }
 
+template <int EPI, int RPT, int STAGES, int CTAS>
+static void launch_spmv_tma_cfg(const Ctx &ctx, const DeviceCsr &A, double alpha, const double *x,
+                                double beta, const double *y_in, double *y_out,
+                                const double *dot_with, double *result, int32_t red_rows,
+                                const int32_t *stop)
+{
+    using Smem = SpmvSmem<RPT, STAGES>;
+    static bool configured[64] = {};
+    if (!configured[ctx.device]) {
+        SCHWZ_CUDA(cudaFuncSetAttribute(csr_spmv_tma_kernel<EPI, RPT, STAGES, CTAS>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)sizeof(Smem)));
+        configured[ctx.device] = true;
+    }
+    const int grid = std::min<int>(A.nblocks, kNumSMs * CTAS);
+    csr_spmv_tma_kernel<EPI, RPT, STAGES, CTAS><<<grid, kSpmvThreads, sizeof(Smem), ctx.stream>>>(
+        A.nblocks, A.blk_row, A.rp, A.ci, A.v, x, alpha, beta, y_in, y_out, dot_with, ctx.partials,
+        ctx.tickets + 0, result, red_rows, stop);
+}
+
 template <int EPI>
 static void launch_spmv_tma(const Ctx &ctx, const DeviceCsr &A, double alpha, const double *x,
                             double beta, const double *y_in, double *y_out, const double *dot_with,
                             double *result, int32_t red_rows, const int32_t *stop)
 {
-    static bool configured[64] = {};
-    if (!configured[ctx.device]) {
-        SCHWZ_CUDA(cudaFuncSetAttribute(csr_spmv_tma_kernel<EPI>,
-                                        cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)sizeof(SpmvSmem)));
-        configured[ctx.device] = true;
+#define SCHWZ_TMA(RPT, ST, CT)                                                                  \
+    launch_spmv_tma_cfg<EPI, RPT, ST, CT>(ctx, A, alpha, x, beta, y_in, y_out, dot_with, result, \
+                                          red_rows, stop)
+    // g_spmv_variant picks the launch shape for a given rows_per_tile
+    if (A.rows_per_tile == kBlock) {
+        switch (g_spmv_variant) {
+        case 0: SCHWZ_TMA(1, 3, 2); break;
+        case 2: SCHWZ_TMA(1, 4, 2); break;
+        default: SCHWZ_TMA(1, 2, 4); break;   // measured best: 0.946 of HBM peak (profiles/)
+        }
+    } else {
+        switch (g_spmv_variant) {
+        case 4: SCHWZ_TMA(2, 3, 1); break;
+        default: SCHWZ_TMA(2, 2, 2); break;
+        }
     }
-    const int grid = std::min<int>(A.nblocks, kNumSMs * kSpmvCtasPerSM);
-    csr_spmv_tma_kernel<EPI><<<grid, kSpmvThreads, sizeof(SpmvSmem), ctx.stream>>>(
-        A.nblocks, A.blk_row, A.rp, A.ci, A.v, x, alpha, beta, y_in, y_out, dot_with, ctx.partials,
-        ctx.tickets + 0, result, red_rows, stop);
+#undef SCHWZ_TMA
 }
 
 void launch_spmv(const Ctx &ctx, const DeviceCsr &A, double alpha, const double *x,
@@ -619,6 +694,10 @@ void launch_cg_init(const Ctx &ctx, CgScalars *s, int32_t max_iters, double tol,
 }
 
 // step_1: p = r + (rho/prev_rho) p   (prev_rho == 0 or first iteration: p = r)
+// Vector kernels keep kVecUnroll independent 16-byte loads per operand in
+// flight per thread (the loads of a trip are all issued before the first use).
+constexpr int kVecUnroll = 4;
+
 __global__ void __launch_bounds__(kBlock)
     cg_p_update_kernel(int64_t n, const double *__restrict__ r, double *__restrict__ p,
                        const CgScalars *__restrict__ s)
@@ -629,16 +708,29 @@ __global__ void __launch_bounds__(kBlock)
     const int64_t n2 = n >> 1;
     const double2 *r2 = reinterpret_cast<const double2 *>(r);
     double2 *p2 = reinterpret_cast<double2 *>(p);
-    for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n2;
-         i += (int64_t)gridDim.x * kBlock) {
-        double2 rv = r2[i];
-        if (fresh) {
-            p2[i] = rv;
-        } else {
-            double2 pv = p2[i];
-            pv.x = rv.x + t * pv.x;
-            pv.y = rv.y + t * pv.y;
-            p2[i] = pv;
+    const int64_t stride = (int64_t)gridDim.x * kBlock * kVecUnroll;
+    for (int64_t i0 = (int64_t)blockIdx.x * kBlock * kVecUnroll + threadIdx.x; i0 < n2; i0 += stride) {
+        double2 rv[kVecUnroll], pv[kVecUnroll];
+#pragma unroll
+        for (int j = 0; j < kVecUnroll; ++j) {
+            const int64_t i = i0 + (int64_t)j * kBlock;
+            if (i < n2) {
+                rv[j] = __ldcs(r2 + i);
+                if (!fresh) pv[j] = p2[i];
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < kVecUnroll; ++j) {
+            const int64_t i = i0 + (int64_t)j * kBlock;
+            if (i < n2) {
+                if (fresh) {
+                    p2[i] = rv[j];
+                } else {
+                    pv[j].x = rv[j].x + t * pv[j].x;
+                    pv[j].y = rv[j].y + t * pv[j].y;
+                    p2[i] = pv[j];
+                }
+            }
         }
     }
     if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0)
@@ -670,19 +762,37 @@ __global__ void __launch_bounds__(kBlock)
     double2 *r2 = reinterpret_cast<double2 *>(r);
     const double2 *p2 = reinterpret_cast<const double2 *>(p);
     const double2 *q2 = reinterpret_cast<const double2 *>(q);
-    for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n2;
-         i += (int64_t)gridDim.x * kBlock) {
-        double2 rv = r2[i];
-        if (!skip) {
-            double2 xv = x2[i], pv = p2[i], qv = q2[i];
-            xv.x += a * pv.x;
-            xv.y += a * pv.y;
-            rv.x -= a * qv.x;
-            rv.y -= a * qv.y;
-            x2[i] = xv;
-            r2[i] = rv;
+    constexpr int U = 2;   // 4 operands x 2 = 8 independent 16-byte loads per trip
+    const int64_t stride = (int64_t)gridDim.x * kBlock * U;
+    for (int64_t i0 = (int64_t)blockIdx.x * kBlock * U + threadIdx.x; i0 < n2; i0 += stride) {
+        double2 rv[U], xv[U], pv[U], qv[U];
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+            const int64_t i = i0 + (int64_t)j * kBlock;
+            if (i < n2) {
+                rv[j] = r2[i];
+                if (!skip) {
+                    xv[j] = x2[i];
+                    pv[j] = p2[i];
+                    qv[j] = __ldcs(q2 + i);
+                }
+            }
         }
-        acc += rv.x * rv.x + rv.y * rv.y;
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+            const int64_t i = i0 + (int64_t)j * kBlock;
+            if (i < n2) {
+                if (!skip) {
+                    xv[j].x += a * pv[j].x;
+                    xv[j].y += a * pv[j].y;
+                    rv[j].x -= a * qv[j].x;
+                    rv[j].y -= a * qv[j].y;
+                    x2[i] = xv[j];
+                    r2[i] = rv[j];
+                }
+                acc += rv[j].x * rv[j].x + rv[j].y * rv[j].y;
+            }
+        }
     }
     if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
         double rv = r[n - 1];

@@ -635,6 +635,37 @@ class Ras:
         return out.value
 
 
+def mailbox_layout(in_total, n_in, P):
+    """Layout of a subdomain's peer-visible mailbox from its index-set sizes
+    (host only; the same function the device side uses)."""
+    lay = MailboxLayout()
+    _chk(load().schwz_b200_mailbox_layout(C.c_int64(in_total), C.c_int32(n_in), C.c_int32(P),
+                                          C.byref(lay)))
+    return lay
+
+
+def remote_connection_plan(setup, my_ranks, nbr_in_of):
+    """Which peer mailboxes the subdomains of this process must be connected to.
+
+    Replaces the MPI handshake + MPI_Alltoall of displacement tables
+    (source/restricted_schwarz.cpp:400-472, 624-658) for the one-process-per-GPU
+    launch: every process holds the index sets, so the plan is computed locally
+    and only the mailbox handles travel.  nbr_in_of[q] = neighbors_in list of
+    subdomain q (from its owner).  Returns tuples
+    (rank, j_out, q, recv_offset_elems, flag_slot) for every out-neighbour q that
+    lives in another process."""
+    plan = []
+    mine = set(my_ranks)
+    for r in my_ranks:
+        _, nout = setup.neighbors(r)
+        pd, _ = setup.displacements(r)
+        for j, q in enumerate(nout.tolist()):
+            if q in mine:
+                continue
+            plan.append((r, j, q, int(pd[q]), list(nbr_in_of[q]).index(r)))
+    return plan
+
+
 def connect_local(subs, setup):
     arr = (C.c_void_p * len(subs))(*[s.h for s in subs])
     _chk(load().schwz_b200_ras_connect_local(arr, C.c_int32(len(subs)), setup.h))
