@@ -289,8 +289,8 @@ def main():
     s0 = subs[min(1, len(subs) - 1)]
     roof = {}
     kern = {}
-    for kind, name in ((0, "csr_spmv_stream_kernel<EPI_DOT>"), (1, "cg_xr_update_kernel"),
-                       (2, "cg_p_update_kernel"), (3, "csr_spmv_stream_kernel<EPI_NRM2>")):
+    for kind, name in ((0, "csr_spmv_tma_kernel<EPI_DOT>"), (1, "cg_xr_update_kernel"),
+                       (2, "cg_p_update_kernel"), (3, "csr_spmv_tma_kernel<EPI_NRM2>")):
         kms = s0.kernel_time_ms(kind, 20)
         kb = s0.kernel_bytes(kind)
         kern[name] = {"ms": kms, "bytes": kb, "GB/s": kb / (kms * 1e-3) / 1e9}
@@ -300,17 +300,17 @@ def main():
         peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)"
     else:
         peak, peak_src = 6650.0, "B200_PROFILING.md fallback (of fallback)"
-    k0 = kern["csr_spmv_stream_kernel<EPI_DOT>"]
+    k0 = kern["csr_spmv_tma_kernel<EPI_DOT>"]
     traffic = None
     tp = os.path.join(ROOT, "profiles", "spmv_traffic.json")
     if os.path.exists(tp):
         traffic = json.load(open(tp)).get("dram_bytes_per_launch")
     per_step_spmv_ms = k0["ms"] * args.local_iters * nl
-    roof = {"bound": "hbm", "kernel": "csr_spmv_stream_kernel<EPI_DOT> (q = A p, p.q fused)",
+    roof = {"bound": "hbm", "kernel": "csr_spmv_tma_kernel<EPI_DOT> (CG: q = A p, p.q fused)",
             "achieved": k0["GB/s"], "peak": peak, "unit": "GB/s", "frac": k0["GB/s"] / peak,
             "traffic": traffic, "peak_source": peak_src, "bytes_per_launch": k0["bytes"],
             "launch_ms": k0["ms"], "share_of_step": per_step_spmv_ms / (ms / args.steps),
-            "other_kernels": {k: v for k, v in kern.items() if k != "csr_spmv_stream_kernel<EPI_DOT>"}}
+            "other_kernels": {k: v for k, v in kern.items() if k != "csr_spmv_tma_kernel<EPI_DOT>"}}
 
     # ---- e2e: the plugin call with HOST buffers ------------------------------
     # rhs (pinned host) -> device, zero initial state, K outer iterations (each
