@@ -63,6 +63,8 @@ int schwz_b200_ctx_create(int device, schwz_ctx **out)
     g_force_simple_spmv = e && e[0] == '1';
     const char *vr = std::getenv("SCHWZ_B200_SPMV_VARIANT");
     if (vr) g_spmv_variant = std::atoi(vr);
+    const char *ns = std::getenv("SCHWZ_B200_NO_SMALL");
+    g_use_small_solvers = !(ns && ns[0] == '1');
     *out = new schwz_ctx(device);
     ABI_END
 }

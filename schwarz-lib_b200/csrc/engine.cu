@@ -214,13 +214,23 @@ Ras::~Ras()
 void Ras::upload_rhs(const double *host_rhs_global)
 {
     ctx.use();
-    if (!pinned_rhs_)
-        SCHWZ_CUDA(cudaMallocHost((void **)&pinned_rhs_, sizeof(double) * (size_t)local_size_x));
-    // own block is contiguous in the global numbering; overlap rows are gathered
-    std::memcpy(pinned_rhs_, host_rhs_global + first_row, sizeof(double) * (size_t)local_size);
-    for (int32_t k = local_size; k < local_size_x; ++k) pinned_rhs_[k] = host_rhs_global[l2g_local_[k]];
-    SCHWZ_CUDA(cudaMemcpyAsync(local_rhs, pinned_rhs_, sizeof(double) * (size_t)local_size_x,
-                               cudaMemcpyHostToDevice, ctx.stream));
+    // Only the overlap rows need a gather (small pinned staging area); the own
+    // block is contiguous in the global numbering and is copied straight from
+    // the caller's buffer (truly asynchronous when that buffer is pinned).
+    if (overlap_size > 0) {
+        if (!pinned_rhs_)
+            SCHWZ_CUDA(cudaMallocHost((void **)&pinned_rhs_, sizeof(double) * (size_t)overlap_size));
+        else
+            SCHWZ_CUDA(cudaStreamSynchronize(ctx.stream));   // staging area still in use?
+        for (int32_t k = 0; k < overlap_size; ++k)
+            pinned_rhs_[k] = host_rhs_global[l2g_local_[local_size + k]];
+        SCHWZ_CUDA(cudaMemcpyAsync(local_rhs + local_size, pinned_rhs_,
+                                   sizeof(double) * (size_t)overlap_size, cudaMemcpyHostToDevice,
+                                   ctx.stream));
+    }
+    SCHWZ_CUDA(cudaMemcpyAsync(local_rhs, host_rhs_global + first_row,
+                               sizeof(double) * (size_t)local_size, cudaMemcpyHostToDevice,
+                               ctx.stream));
 }
 
 void Ras::download_solution(double *host_solution_global)

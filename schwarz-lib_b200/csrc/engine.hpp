@@ -22,6 +22,16 @@ void comm_unique_id(void *id128);
 Comm *comm_create(const Ctx &ctx, const void *id128, int nranks, int rank);
 void comm_allgather_f64(Comm &c, const double *dev_in, int count, double *dev_out);
 
+// one-CTA solvers for small subdomains (small_solvers.cu)
+extern bool g_use_small_solvers;   // SCHWZ_B200_NO_SMALL=1 turns them off (A/B measurements)
+bool cg_small_fits(int64_t n);
+void launch_cg_small(const Ctx &ctx, const DeviceCsr &A, const double *b, double *x,
+                     int32_t max_iters, double tol, CgScalars *out, const int32_t *outer_stop);
+bool gmres_small_fits(int64_t n, int m);
+void launch_gmres_small(const Ctx &ctx, const DeviceCsr &A, const double *b, double *x, double *V,
+                        int32_t m, int32_t max_iters, double tol, double *resnorm_out,
+                        double *r0_out, int32_t *total_out);
+
 // ---- CG (Ginkgo Cg semantics; source/solve.cpp:469-478, 572-652, 746-754) ----
 class CgSolver {
 public:

@@ -1,0 +1,289 @@
+// One-launch local solvers for small subdomains (configurations 1 and 3 of
+// BASELINE.json: 400..5100 rows per subdomain).  At that size a Krylov
+// iteration is a few microseconds of work, so the multi-kernel solvers in
+// solvers.cu are bound by launch latency (3 launches per CG iteration,
+// 2k+7 per GMRES step).  Here ONE CTA of 1024 threads runs the whole solve:
+// vectors live in shared memory (CG) or in L2-resident global memory (the
+// GMRES basis), reductions are fixed-shape CTA reductions, the matrix streams
+// from L1/L2, and the recurrences / stopping rules are exactly those of
+// solvers.cu (Ginkgo semantics).  Rows are summed
+// sequentially in stored order, as everywhere else.
+#include <algorithm>
+
+#include "engine.hpp"
+
+namespace schwz_b200 {
+
+constexpr int kSmallThreads = 1024;
+constexpr int kSmallWarps = kSmallThreads / 32;
+
+__device__ __forceinline__ double cta_sum(double v, double *buf /* kSmallWarps + 1 */)
+{
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    v = warp_sum(v);
+    __syncthreads();   // buf may still be read from the previous reduction
+    if (lane == 0) buf[w] = v;
+    __syncthreads();
+    if (w == 0) {
+        double s = lane < kSmallWarps ? buf[lane] : 0.0;
+        s = warp_sum(s);
+        if (lane == 0) buf[kSmallWarps] = s;
+    }
+    __syncthreads();
+    return buf[kSmallWarps];
+}
+
+__device__ __forceinline__ double row_dot(const int32_t *__restrict__ rp,
+                                          const int32_t *__restrict__ ci,
+                                          const double *__restrict__ v, const double *xs, int32_t row)
+{
+    double acc = 0.0;
+    for (int32_t k = rp[row]; k < rp[row + 1]; ++k) acc += __ldg(v + k) * xs[__ldg(ci + k)];
+    return acc;
+}
+
+// -----------------------------------------------------------------------------
+// CG: x, r, p, q in shared memory.
+// -----------------------------------------------------------------------------
+__global__ void __launch_bounds__(kSmallThreads, 1)
+    cg_small_kernel(int32_t n, const int32_t *__restrict__ rp, const int32_t *__restrict__ ci,
+                    const double *__restrict__ v, const double *__restrict__ b, double *x,
+                    int32_t max_iters, double tol, CgScalars *out, const int32_t *outer_stop)
+{
+    extern __shared__ __align__(16) double sm[];
+    double *xs = sm, *r = sm + n, *p = sm + 2 * (size_t)n, *q = sm + 3 * (size_t)n;
+    double *buf = sm + 4 * (size_t)n;
+    if (outer_stop != nullptr && *outer_stop != 0) return;
+    const int t = threadIdx.x;
+    for (int32_t i = t; i < n; i += kSmallThreads) {
+        xs[i] = x[i];
+        p[i] = 0.0;
+    }
+    __syncthreads();
+    double part = 0.0;
+    for (int32_t i = t; i < n; i += kSmallThreads) {
+        // r = b - A x  (same expression order as the advanced SpMV: beta*y first)
+        double acc = b[i];
+        for (int32_t k = rp[i]; k < rp[i + 1]; ++k) acc += (-__ldg(v + k)) * xs[__ldg(ci + k)];
+        r[i] = acc;
+        part += acc * acc;
+    }
+    double rho = cta_sum(part, buf);
+    const double r0 = sqrt(rho);
+    double prev_rho = 1.0, resnorm = r0;
+    int iter = 0;
+    while (true) {
+        if (iter >= max_iters || resnorm < tol * r0) break;
+        const bool fresh = (iter == 0) || (prev_rho == 0.0);
+        const double tp = fresh ? 0.0 : rho / prev_rho;
+        for (int32_t i = t; i < n; i += kSmallThreads) p[i] = fresh ? r[i] : r[i] + tp * p[i];
+        __syncthreads();
+        part = 0.0;
+        for (int32_t i = t; i < n; i += kSmallThreads) {
+            const double qi = row_dot(rp, ci, v, p, i);
+            q[i] = qi;
+            part += qi * p[i];
+        }
+        const double beta = cta_sum(part, buf);
+        part = 0.0;
+        if (beta != 0.0) {
+            const double a = rho / beta;
+            for (int32_t i = t; i < n; i += kSmallThreads) {
+                xs[i] += a * p[i];
+                const double ri = r[i] - a * q[i];
+                r[i] = ri;
+                part += ri * ri;
+            }
+        } else {
+            for (int32_t i = t; i < n; i += kSmallThreads) part += r[i] * r[i];
+        }
+        const double rho_new = cta_sum(part, buf);
+        prev_rho = rho;
+        rho = rho_new;
+        ++iter;
+        resnorm = sqrt(rho_new);
+    }
+    __syncthreads();
+    for (int32_t i = t; i < n; i += kSmallThreads) x[i] = xs[i];
+    if (t == 0) {
+        out->rho = rho;
+        out->prev_rho = prev_rho;
+        out->r0 = r0;
+        out->resnorm = resnorm;
+        out->tol = tol;
+        out->iter = iter;
+        out->max_iters = max_iters;
+        out->stop = 1;
+    }
+}
+
+bool cg_small_fits(int64_t n) { return n > 0 && (4 * n + kSmallWarps + 8) * 8 <= 220 * 1024; }
+
+void launch_cg_small(const Ctx &ctx, const DeviceCsr &A, const double *b, double *x,
+                     int32_t max_iters, double tol, CgScalars *out, const int32_t *outer_stop)
+{
+    ctx.use();
+    const size_t smem = (4 * (size_t)A.nrows + kSmallWarps + 8) * sizeof(double);
+    static bool configured[64] = {};
+    if (!configured[ctx.device]) {
+        SCHWZ_CUDA(cudaFuncSetAttribute(cg_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        220 * 1024));
+        configured[ctx.device] = true;
+    }
+    cg_small_kernel<<<1, kSmallThreads, smem, ctx.stream>>>(A.nrows, A.rp, A.ci, A.v, b, x, max_iters,
+                                                            tol, out, outer_stop);
+    SCHWZ_CUDA(cudaGetLastError());
+    count_launch();
+}
+
+// -----------------------------------------------------------------------------
+// GMRES(m): w and the small Hessenberg system in shared memory, the Krylov
+// basis V ((m+1) x n) in global memory (L2 resident at these sizes).
+// -----------------------------------------------------------------------------
+__global__ void __launch_bounds__(kSmallThreads, 1)
+    gmres_small_kernel(int32_t n, const int32_t *__restrict__ rp, const int32_t *__restrict__ ci,
+                       const double *__restrict__ v, const double *__restrict__ b, double *x,
+                       double *V, int32_t m, int32_t max_iters, double tol, double *resnorm_out,
+                       double *r0_out, int32_t *total_out)
+{
+    extern __shared__ __align__(16) double sm[];
+    double *w = sm;                               // n
+    double *H = w + n;                            // (m+1)*m, column-major
+    double *cs = H + (size_t)(m + 1) * m;         // m
+    double *sn = cs + m;                          // m
+    double *g = sn + m;                           // m+1
+    double *y = g + m + 1;                        // m
+    double *buf = y + m;                          // kSmallWarps+1
+    const int t = threadIdx.x;
+
+    // r = b - A x ; ||r|| ; V0 = r / ||r||   (x read from global: it changes at restarts)
+    auto begin_cycle = [&]() -> double {
+        __syncthreads();
+        double part = 0.0;
+        for (int32_t i = t; i < n; i += kSmallThreads) {
+            double acc = b[i];
+            for (int32_t k = rp[i]; k < rp[i + 1]; ++k) acc += (-__ldg(v + k)) * x[__ldg(ci + k)];
+            w[i] = acc;
+            part += acc * acc;
+        }
+        const double rn = sqrt(cta_sum(part, buf));
+        for (int32_t i = t; i < n; i += kSmallThreads) V[i] = rn != 0.0 ? w[i] / rn : 0.0;
+        if (t == 0) {
+            for (int i = 0; i <= m; ++i) g[i] = 0.0;
+            g[0] = rn;
+        }
+        __syncthreads();
+        return rn;
+    };
+    // x += V(:, 0:k) y  with  H(0:k,0:k) y = g(0:k)
+    auto update_x = [&](int k) {
+        __syncthreads();
+        if (t == 0) {
+            for (int i = k - 1; i >= 0; --i) {
+                double s = g[i];
+                for (int j = i + 1; j < k; ++j) s -= H[(size_t)j * (m + 1) + i] * y[j];
+                y[i] = s / H[(size_t)i * (m + 1) + i];
+            }
+        }
+        __syncthreads();
+        for (int32_t i = t; i < n; i += kSmallThreads) {
+            double xv = x[i];
+            for (int j = 0; j < k; ++j) xv += y[j] * V[(size_t)j * n + i];
+            x[i] = xv;
+        }
+        __syncthreads();
+    };
+
+    double resnorm = begin_cycle();
+    const double r0 = resnorm;
+    int total = -1, k = 0;
+    while (true) {
+        ++total;
+        if (total >= max_iters || resnorm < tol * r0) break;
+        if (k == m) {
+            update_x(k);
+            resnorm = begin_cycle();
+            k = 0;
+        }
+        // w = A V_k  (V_k read through a shared copy: stage it in w's place is not
+        // possible, so rows gather from global/L2)
+        const double *vk = V + (size_t)k * n;
+        for (int32_t i = t; i < n; i += kSmallThreads) {
+            double acc = 0.0;
+            for (int32_t q = rp[i]; q < rp[i + 1]; ++q) acc += __ldg(v + q) * vk[__ldg(ci + q)];
+            w[i] = acc;
+        }
+        double *col = H + (size_t)k * (m + 1);
+        for (int i = 0; i <= k; ++i) {   // modified Gram-Schmidt
+            const double *vi = V + (size_t)i * n;
+            double part = 0.0;
+            for (int32_t j = t; j < n; j += kSmallThreads) part += w[j] * vi[j];
+            const double h = cta_sum(part, buf);
+            if (t == 0) col[i] = h;
+            for (int32_t j = t; j < n; j += kSmallThreads) w[j] += (-h) * vi[j];
+        }
+        double part = 0.0;
+        for (int32_t j = t; j < n; j += kSmallThreads) part += w[j] * w[j];
+        const double hn = sqrt(cta_sum(part, buf));
+        double *vn = V + (size_t)(k + 1) * n;
+        for (int32_t j = t; j < n; j += kSmallThreads) vn[j] = hn != 0.0 ? w[j] / hn : 0.0;
+        if (t == 0) {
+            col[k + 1] = hn;
+            for (int i = 0; i < k; ++i) {
+                const double tt = cs[i] * col[i] + sn[i] * col[i + 1];
+                col[i + 1] = -sn[i] * col[i] + cs[i] * col[i + 1];
+                col[i] = tt;
+            }
+            const double a = col[k], c = col[k + 1];
+            if (a == 0.0) {
+                cs[k] = 0.0;
+                sn[k] = 1.0;
+            } else {
+                const double sc = fabs(a) + fabs(c);
+                const double hyp = sc * sqrt((a / sc) * (a / sc) + (c / sc) * (c / sc));
+                cs[k] = a / hyp;
+                sn[k] = c / hyp;
+            }
+            col[k] = cs[k] * a + sn[k] * c;
+            col[k + 1] = 0.0;
+            g[k + 1] = -sn[k] * g[k];
+            g[k] = cs[k] * g[k];
+            buf[kSmallWarps + 1] = fabs(g[k + 1]);
+        }
+        __syncthreads();   // also makes V_{k+1} (global) visible to the whole CTA
+        resnorm = buf[kSmallWarps + 1];
+        ++k;
+    }
+    update_x(k);
+    if (t == 0) {
+        *resnorm_out = resnorm;
+        *r0_out = r0;
+        *total_out = total;
+    }
+}
+
+static size_t gmres_small_smem(int64_t n, int m)
+{
+    return ((size_t)n + (size_t)(m + 1) * m + 4 * (size_t)m + 1 + kSmallWarps + 8) * sizeof(double);
+}
+
+bool gmres_small_fits(int64_t n, int m) { return n > 0 && n <= 16384 && gmres_small_smem(n, m) <= 220 * 1024; }
+
+void launch_gmres_small(const Ctx &ctx, const DeviceCsr &A, const double *b, double *x, double *V,
+                        int32_t m, int32_t max_iters, double tol, double *resnorm_out,
+                        double *r0_out, int32_t *total_out)
+{
+    ctx.use();
+    static bool configured[64] = {};
+    if (!configured[ctx.device]) {
+        SCHWZ_CUDA(cudaFuncSetAttribute(gmres_small_kernel,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        configured[ctx.device] = true;
+    }
+    gmres_small_kernel<<<1, kSmallThreads, gmres_small_smem(A.nrows, m), ctx.stream>>>(
+        A.nrows, A.rp, A.ci, A.v, b, x, V, m, max_iters, tol, resnorm_out, r0_out, total_out);
+    SCHWZ_CUDA(cudaGetLastError());
+    count_launch();
+}
+
+}  // namespace schwz_b200

@@ -12,6 +12,8 @@ namespace schwz_b200 {
 // =============================================================================
 // CG
 // =============================================================================
+bool g_use_small_solvers = true;
+
 constexpr int kCgNoPoll = 160;   // up to this many iterations: enqueue all, never poll
 constexpr int kCgChunk = 32;     // otherwise poll the stop flag once per chunk
 
@@ -56,6 +58,11 @@ void CgSolver::solve(const double *b, double *x, int32_t max_iters, double tol,
                      const int32_t *outer_stop)
 {
     SCHWZ_REQUIRE(((uintptr_t)x & 15) == 0, "CG solution vector must be 16-byte aligned");
+    if (g_use_small_solvers && cg_small_fits(n_)) {
+        // whole solve in one launch (small_solvers.cu)
+        launch_cg_small(ctx_, A_, b, x, max_iters, tol, s_, outer_stop);
+        return;
+    }
     // r = b - A x, rho = r.r fused
     launch_spmv(ctx_, A_, -1.0, x, 1.0, b, r_, EPI_NRM2SQ, nullptr, &s_->rho, (int32_t)n_,
                 outer_stop);
@@ -293,6 +300,10 @@ void GmresSolver::solve(const double *b, double *x, int32_t max_iters, double to
     GmresState *S = (GmresState *)(small_ + small);
     double *H = small_;
     const int g = vgrid(n_);
+    if (g_use_small_solvers && gmres_small_fits(n_, m_)) {
+        launch_gmres_small(ctx_, A_, b, x, V_, m_, max_iters, tol, &S->resnorm, &S->r0, &S->total);
+        return;
+    }
 
     auto begin_cycle = [&](int first) {
         // w = b - A x ; tmp = ||w|| ; V0 = w / ||w||

@@ -152,8 +152,10 @@ def test_blas1_and_gather_scatter(gpu, sz):
 
 
 def test_cg_matches_oracle(gpu, sz, orc, ani4):
+    """40x40 and ani4 run the one-CTA solver (small_solvers.cu); 120x120 (14 400
+    rows) is above its shared-memory limit and runs the multi-kernel solver."""
     rng = np.random.default_rng(5)
-    for (rp, ci, v) in (orc.laplacian2d(40), ani4):
+    for (rp, ci, v) in (orc.laplacian2d(40), ani4, orc.laplacian2d(120)):
         n = len(rp) - 1
         A = sz.Csr(gpu, rp, ci, v)
         cg = sz.Cg(gpu, A)
@@ -210,6 +212,22 @@ def test_gmres_matches_oracle(gpu, sz, orc, ani4):
         assert it == ito == K
         np.testing.assert_allclose(gpu.to_host(dx, n), xo, rtol=1e-9, atol=1e-11)
         gpu.free(dx); g.close()
+    # above the one-CTA limit (16 384 rows): the multi-kernel GMRES
+    rpL, ciL, vL = orc.laplacian2d(130)
+    nL = len(rpL) - 1
+    AL = sz.Csr(gpu, rpL, ciL, vL)
+    bL = rng.standard_normal(nL)
+    dbL = gpu.to_device(bL)
+    for m, K in ((5, 12), (20, 45)):
+        g = sz.Gmres(gpu, AL, m)
+        dx = gpu.zeros(nL)
+        g.solve(dbL, dx, K, 1e-300)
+        it, rn, r0 = g.result()
+        xo, ito = orc.gmres(rpL, ciL, vL, bL, np.zeros(nL), K, 1e-300, m)
+        assert it == ito == K
+        np.testing.assert_allclose(gpu.to_host(dx, nL), xo, rtol=1e-9, atol=1e-11)
+        gpu.free(dx); g.close()
+    gpu.free(dbL); AL.close()
     g = sz.Gmres(gpu, A, 30)
     dx = gpu.zeros(n)
     g.solve(db, dx, 3000, 1e-10)
