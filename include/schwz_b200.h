@@ -225,13 +225,17 @@ typedef struct {
     int64_t flags_off;     /* u64 epoch word per in-neighbour       */
     int64_t conv_off;      /* P int32 convergence flags             */
     int64_t err_off;       /* int32 error word                      */
+    int64_t send_off;      /* send buffer, sum(out-list lengths) doubles: window_send_buffer
+                            * of the reference (restricted_schwarz.cpp:549-568)            */
+    int64_t slots_off;     /* int32 per received element: its slot in x (local_get + 1)    */
+    int64_t x_off;         /* x = [own | overlap | halo] itself: window_x (:661-667)       */
     int64_t bytes;
 } schwz_mailbox_layout;
 int schwz_b200_ras_mailbox(schwz_ras *r, void **dev_base, schwz_mailbox_layout *layout);
-/* host only: the layout implied by the index-set sizes (in_total = sum of the
- * in-list lengths, n_in = num_neighbors_in) */
-int schwz_b200_mailbox_layout(int64_t in_total, int32_t n_in, int32_t P,
-                              schwz_mailbox_layout *layout);
+/* host only: the layout implied by the index-set sizes (in_total / out_total = sum of
+ * the in- / out-list lengths, n_in = num_neighbors_in, x_len = local_size_x + n_halo) */
+int schwz_b200_mailbox_layout(int64_t in_total, int32_t n_in, int32_t P, int64_t out_total,
+                              int64_t x_len, schwz_mailbox_layout *layout);
 /* sizes a peer needs: out[0] = num_neighbors_in, out[1] = num_neighbors_out,
  * out[2] = local_size, out[3] = local_size_x, out[4] = n_halo, out[5] = nnz_local */
 int schwz_b200_ras_info(schwz_ras *r, int64_t *out);
@@ -246,7 +250,20 @@ int schwz_b200_ras_connect(schwz_ras *r, int32_t j_out, void *peer_mailbox_base,
                            const schwz_mailbox_layout *peer_layout,
                            int32_t peer_recv_offset_elems, int32_t peer_flag_slot,
                            int32_t same_process);
-/* connects every pair of subdomains living in this process */
+/* Get variants: tell subdomain r where in-neighbour j's mailbox lives;
+ * peer_send_offset_elems = get_displacements[neighbour]
+ * (source/restricted_schwarz.cpp:642-658). */
+int schwz_b200_ras_connect_in(schwz_ras *r, int32_t j_in, void *peer_mailbox_base,
+                              const schwz_mailbox_layout *peer_layout,
+                              int32_t peer_send_offset_elems);
+/* centralised-tree convergence: parent and children need not be halo neighbours */
+int schwz_b200_ras_connect_conv(schwz_ras *r, int32_t peer_rank, void *peer_mailbox_base,
+                                const schwz_mailbox_layout *peer_layout);
+/* Settings::comm_settings enable_put/enable_get x enable_one_by_one
+ * (source/restricted_schwarz.cpp:753-851): 0 Put gathered (also the synchronous
+ * exchange), 1 Get gathered, 2 Put one-by-one, 3 Get one-by-one. */
+int schwz_b200_ras_set_exchange_mode(schwz_ras *r, int32_t mode);
+/* connects every pair of subdomains living in this process (out, in and conv) */
 int schwz_b200_ras_connect_local(schwz_ras **subdomains, int32_t n_local, schwz_setup *s);
 /* loop stages (asynchronous on the subdomain's stream) */
 int schwz_b200_ras_exchange_push(schwz_ras *r, int32_t iter);
@@ -285,6 +302,9 @@ int schwz_b200_ras_true_residual_sq(schwz_ras *r, double *host_out);
 /* decentralised convergence flags (include/conv_tools.hpp:213-275) */
 int schwz_b200_ras_conv_set_local(schwz_ras *r, int32_t converged_all_local);
 int schwz_b200_ras_conv_forward(schwz_ras *r);
+/* centralised binary tree (include/conv_tools.hpp:147-209): push up to the parent once the
+ * children have, the root pushes down; conv_count then returns P or 0 */
+int schwz_b200_ras_conv_tree(schwz_ras *r, int32_t converged_all_local);
 int schwz_b200_ras_conv_count(schwz_ras *r, int32_t *num_converged);  /* synchronises */
 
 /* ---- whole outer loop over the subdomains of this process --------------------
@@ -298,7 +318,7 @@ typedef struct {
     int32_t enable_global_check;
     int32_t conv_decentralized;    /* else centralised tree               */
     int32_t iter_offset;
-    int32_t reserved;
+    int32_t exchange_mode;         /* one-sided only, see schwz_b200_ras_set_exchange_mode */
     /* cross-process allgather of the residual norms (ncclAllGather); NULL when
      * every subdomain lives in this process.  Subdomain ids must be spread
      * contiguously and evenly: process r owns ids [r*n_local, (r+1)*n_local). */

@@ -591,17 +591,24 @@ int schwz_b200_ras_mailbox(schwz_ras *r, void **base, schwz_mailbox_layout *l)
     l->flags_off = r->impl->mbox.flags_off;
     l->conv_off = r->impl->mbox.conv_off;
     l->err_off = r->impl->mbox.err_off;
+    l->send_off = r->impl->mbox.send_off;
+    l->slots_off = r->impl->mbox.slots_off;
+    l->x_off = r->impl->mbox.x_off;
     l->bytes = r->impl->mbox.bytes;
     ABI_END
 }
-int schwz_b200_mailbox_layout(int64_t in_total, int32_t n_in, int32_t P, schwz_mailbox_layout *l)
+int schwz_b200_mailbox_layout(int64_t in_total, int32_t n_in, int32_t P, int64_t out_total,
+                              int64_t x_len, schwz_mailbox_layout *l)
 {
     ABI_BEGIN
-    MailboxLayout m = MailboxLayout::make(in_total, n_in, P);
+    MailboxLayout m = MailboxLayout::make(in_total, n_in, P, out_total, x_len);
     l->recv_stride = m.recv_stride;
     l->flags_off = m.flags_off;
     l->conv_off = m.conv_off;
     l->err_off = m.err_off;
+    l->send_off = m.send_off;
+    l->slots_off = m.slots_off;
+    l->x_off = m.x_off;
     l->bytes = m.bytes;
     ABI_END
 }
@@ -623,17 +630,44 @@ int schwz_b200_ras_neighbors(schwz_ras *r, int32_t *nin, int32_t *nout)
     std::copy(r->impl->nbr_out.begin(), r->impl->nbr_out.end(), nout);
     ABI_END
 }
-int schwz_b200_ras_connect(schwz_ras *r, int32_t j, void *peer_base, const schwz_mailbox_layout *l,
-                           int32_t recv_off, int32_t flag_slot, int32_t same_process)
+static MailboxLayout layout_from_abi(const schwz_mailbox_layout *l)
 {
-    ABI_BEGIN
     MailboxLayout m;
     m.recv_stride = l->recv_stride;
     m.flags_off = l->flags_off;
     m.conv_off = l->conv_off;
     m.err_off = l->err_off;
+    m.send_off = l->send_off;
+    m.slots_off = l->slots_off;
+    m.x_off = l->x_off;
     m.bytes = l->bytes;
-    r->impl->connect(j, peer_base, m, recv_off, flag_slot, same_process != 0);
+    return m;
+}
+int schwz_b200_ras_connect(schwz_ras *r, int32_t j, void *peer_base, const schwz_mailbox_layout *l,
+                           int32_t recv_off, int32_t flag_slot, int32_t same_process)
+{
+    ABI_BEGIN
+    r->impl->connect(j, peer_base, layout_from_abi(l), recv_off, flag_slot, same_process != 0);
+    ABI_END
+}
+int schwz_b200_ras_connect_in(schwz_ras *r, int32_t j, void *peer_base, const schwz_mailbox_layout *l,
+                              int32_t send_off)
+{
+    ABI_BEGIN
+    r->impl->connect_in(j, peer_base, layout_from_abi(l), send_off);
+    ABI_END
+}
+int schwz_b200_ras_connect_conv(schwz_ras *r, int32_t peer_rank, void *peer_base,
+                                const schwz_mailbox_layout *l)
+{
+    ABI_BEGIN
+    r->impl->connect_conv(peer_rank, peer_base, layout_from_abi(l));
+    ABI_END
+}
+int schwz_b200_ras_set_exchange_mode(schwz_ras *r, int32_t mode)
+{
+    ABI_BEGIN
+    r->impl->set_exchange_mode(mode);
     ABI_END
 }
 int schwz_b200_ras_connect_local(schwz_ras **subs, int32_t n, schwz_setup *s)
@@ -653,6 +687,17 @@ int schwz_b200_ras_connect_local(schwz_ras **subs, int32_t n, schwz_setup *s)
                 SCHWZ_REQUIRE(slot >= 0, "asymmetric neighbour lists");
                 R.connect((int32_t)j, Q.mailbox, Q.mbox, L.put_disp[q], slot, true);
             }
+        }
+        for (size_t j = 0; j < R.nbr_in.size(); ++j) {
+            const int32_t q = R.nbr_in[j];
+            for (int32_t b = 0; b < n; ++b) {
+                Ras &Q = *subs[b]->impl;
+                if (Q.rank == q) R.connect_in((int32_t)j, Q.mailbox, Q.mbox, L.get_disp[q]);
+            }
+        }
+        for (int32_t b = 0; b < n; ++b) {
+            Ras &Q = *subs[b]->impl;
+            R.connect_conv(Q.rank, Q.mailbox, Q.mbox);
         }
     }
     ABI_END
@@ -806,6 +851,12 @@ int schwz_b200_ras_conv_set_local(schwz_ras *r, int32_t converged_all_local)
     r->impl->conv_forward(converged_all_local);
     ABI_END
 }
+int schwz_b200_ras_conv_tree(schwz_ras *r, int32_t converged_all_local)
+{
+    ABI_BEGIN
+    r->impl->conv_tree(converged_all_local);
+    ABI_END
+}
 int schwz_b200_ras_conv_forward(schwz_ras *r)
 {
     ABI_BEGIN
@@ -836,6 +887,8 @@ int schwz_b200_ras_run(schwz_ras **subs, int32_t n_local, const schwz_loop_optio
     lo.enable_global_check = o->enable_global_check;
     lo.conv_decentralized = o->conv_decentralized;
     lo.iter_offset = o->iter_offset;
+    lo.exchange_mode = o->exchange_mode;
+    lo.conv_tree = (o->enable_onesided && !o->conv_decentralized) ? 1 : 0;
     lo.comm = o->comm ? o->comm->impl.get() : nullptr;
     LoopResult lr;
     ras_run(v, lo, lr, history);

@@ -122,9 +122,19 @@ void launch_halo_unpack(const Ctx &ctx, int32_t nseg, int32_t total, const int32
                         const double *recv, double *x, const unsigned long long *flags,
                         unsigned long long epoch, int32_t *error_flag);
 
+void launch_halo_put_elements(const Ctx &ctx, int32_t nseg, const int32_t *seg_off_dev,
+                              int32_t total, const int32_t *src_idx, const int32_t *remote_slot,
+                              const double *x, double *const *peer_x);
+void launch_halo_pull(const Ctx &ctx, int32_t nseg, const int32_t *seg_off_dev, int32_t total,
+                      const int32_t *dst_idx, const int32_t *src_idx,
+                      const double *const *src_ptrs, double *x);
+
 // convergence flags (include/conv_tools.hpp:248-274 on peer-mapped words)
 void launch_conv_forward(const Ctx &ctx, int32_t P, int32_t me, int32_t converged_all_local,
                          int32_t *conv, int32_t *conv_sent, int32_t n_out,
                          int32_t *const *peer_conv, int32_t *num_converged);
+// centralised tree (include/conv_tools.hpp:147-209); peer_conv indexed by subdomain id
+void launch_conv_tree(const Ctx &ctx, int32_t P, int32_t me, int32_t converged_all_local,
+                      int32_t *conv, int32_t *const *peer_conv, int32_t *num_converged);
 
 }  // namespace schwz_b200

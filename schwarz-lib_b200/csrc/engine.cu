@@ -95,14 +95,18 @@ void comm_allgather_f64(Comm &c, const double *dev_in, int count, double *dev_ou
 // =============================================================================
 static int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
 
-MailboxLayout MailboxLayout::make(int64_t in_total, int32_t n_in, int32_t P)
+MailboxLayout MailboxLayout::make(int64_t in_total, int32_t n_in, int32_t P, int64_t out_total,
+                                  int64_t x_len)
 {
     MailboxLayout m;
     m.recv_stride = align_up(std::max<int64_t>(in_total, 1) * 8, 256);
     m.flags_off = 2 * m.recv_stride;
     m.conv_off = m.flags_off + align_up(std::max(n_in, 1) * 8, 256);
     m.err_off = m.conv_off + align_up((int64_t)std::max(P, 3) * 4, 256);
-    m.bytes = m.err_off + 256;
+    m.send_off = m.err_off + 256;
+    m.slots_off = m.send_off + align_up(std::max<int64_t>(out_total, 1) * 8, 256);
+    m.x_off = m.slots_off + align_up(std::max<int64_t>(in_total, 1) * 4, 256);
+    m.bytes = m.x_off + align_up(std::max<int64_t>(x_len, 1) * 8, 256);
     return m;
 }
 
@@ -138,7 +142,7 @@ Ras::Ras(const Ctx &ctx_, Setup &setup, int32_t rank_, const double *host_rhs_gl
         for (int32_t k = 0; k < local_size_x; ++k) lrhs[k] = host_rhs_global[R.l2g[k]];
     local_rhs = ctx.upload(lrhs.data(), lrhs.size());
     // F8: the reference leaves these uninitialised and relies on zeros
-    x = ctx.alloc_zero<double>((size_t)local_size_x + n_halo);
+    // (x itself lives in the peer-visible mailbox, allocated below)
     local_sol = ctx.alloc_zero<double>(local_size_x);
     init_guess = ctx.alloc_zero<double>(local_size_x);
     work = ctx.alloc_zero<double>(2 * (size_t)local_size_x);
@@ -166,6 +170,17 @@ Ras::Ras(const Ctx &ctx_, Setup &setup, int32_t rank_, const double *host_rhs_gl
         }
         in_total_ = (int32_t)dst.size();
         in_dst_ = ctx.upload(dst.data(), dst.size());
+        // Get one-by-one: where each of those elements sits inside its owner's x (the own
+        // block of a subdomain is stored first, in global order)
+        std::vector<int32_t> rsrc;
+        in_off_host_.assign(1, 0);
+        for (size_t j = 0; j < R.get.size(); ++j) {
+            const int32_t owner_first = setup.first_row()[nbr_in[j]];
+            for (int32_t gid : R.get[j]) rsrc.push_back(gid - owner_first);
+            in_off_host_.push_back((int32_t)rsrc.size());
+        }
+        in_remote_idx_ = ctx.upload(rsrc.data(), rsrc.size());
+        in_off_ = ctx.upload(in_off_host_.data(), in_off_host_.size());
     }
     {
         std::vector<int32_t> src, off(1, 0);
@@ -177,10 +192,31 @@ Ras::Ras(const Ctx &ctx_, Setup &setup, int32_t rank_, const double *host_rhs_gl
         out_total_ = (int32_t)src.size();
         out_src_ = ctx.upload(src.data(), src.size());
         out_off_ = ctx.upload(off.data(), off.size());
+        out_off_host_ = off;
     }
-    mbox = MailboxLayout::make(in_total_, (int32_t)nbr_in.size(), P);
+    mbox = MailboxLayout::make(in_total_, (int32_t)nbr_in.size(), P, out_total_,
+                               (int64_t)local_size_x + n_halo);
     mailbox = ctx.alloc_zero<char>((size_t)mbox.bytes);
+    x = (double *)(mailbox + mbox.x_off);
+    if (in_total_ > 0)   // the slot table is what a one-by-one Put peer needs to know
+        SCHWZ_CUDA(cudaMemcpyAsync(mailbox + mbox.slots_off, in_dst_, sizeof(int32_t) * (size_t)in_total_,
+                                   cudaMemcpyDeviceToDevice, ctx.stream));
     const size_t no = nbr_out.size();
+    const size_t ni = nbr_in.size();
+    out_remote_slot_ = ctx.alloc_zero<int32_t>(std::max<size_t>(out_total_, 1));
+    in_send_host_.assign(ni, nullptr);
+    in_x_host_.assign(ni, nullptr);
+    out_x_host_.assign(no, nullptr);
+    send_seg_host_.assign(no, nullptr);
+    for (size_t j = 0; j < no; ++j)
+        send_seg_host_[j] = (double *)(mailbox + mbox.send_off) + out_off_host_[j];
+    in_send_dev_ = ctx.alloc_zero<const double *>(std::max<size_t>(ni, 1));
+    in_x_dev_ = ctx.alloc_zero<const double *>(std::max<size_t>(ni, 1));
+    out_x_dev_ = ctx.alloc_zero<double *>(std::max<size_t>(no, 1));
+    send_seg_dev_ = ctx.alloc_zero<double *>(std::max<size_t>(no, 1));
+    conv_peer_host_.assign((size_t)P, nullptr);
+    conv_peer_host_[rank] = conv();
+    conv_peer_dev_ = ctx.alloc_zero<int32_t *>((size_t)P);
     for (int b = 0; b < 2; ++b) out_dst_host_[b].assign(no, nullptr);
     out_flag_host_.assign(no, nullptr);
     out_conv_host_.assign(no, nullptr);
@@ -201,7 +237,11 @@ Ras::~Ras()
 {
     cudaSetDevice(ctx.device);
     cudaStreamSynchronize(ctx.stream);
-    for (void *p : {(void *)x, (void *)local_rhs, (void *)local_sol, (void *)init_guess,
+    for (void *p : {(void *)in_off_, (void *)in_remote_idx_, (void *)out_remote_slot_,
+                    (void *)in_send_dev_, (void *)in_x_dev_, (void *)out_x_dev_,
+                    (void *)send_seg_dev_, (void *)conv_peer_dev_})
+        ctx.release(p);
+    for (void *p : {(void *)local_rhs, (void *)local_sol, (void *)init_guess,
                     (void *)work, (void *)resnorm_dev, (void *)num_converged_dev,
                     (void *)conv_sent, (void *)mailbox, (void *)in_dst_, (void *)out_src_,
                     (void *)out_off_, (void *)out_dst_dev_[0], (void *)out_dst_dev_[1],
@@ -316,7 +356,41 @@ void Ras::connect(int32_t j, void *peer_base, const MailboxLayout &pl, int32_t p
     out_flag_host_[j] = (unsigned long long *)(base + pl.flags_off) + peer_flag_slot;
     out_conv_host_[j] = (int32_t *)(base + pl.conv_off);
     out_same_process_[j] = same_process ? 1 : 0;
+    out_x_host_[j] = (double *)(base + pl.x_off);
+    conv_peer_host_[nbr_out[j]] = out_conv_host_[j];
+    // the slots the neighbour keeps my elements in (its scatter table for my block)
+    const int32_t cnt = out_off_host_[j + 1] - out_off_host_[j];
+    if (cnt > 0) {
+        ctx.use();
+        SCHWZ_CUDA(cudaMemcpyAsync(out_remote_slot_ + out_off_host_[j],
+                                   (const int32_t *)(base + pl.slots_off) + peer_recv_offset,
+                                   sizeof(int32_t) * (size_t)cnt, cudaMemcpyDefault, ctx.stream));
+    }
     peer_tables_dirty_ = true;
+}
+
+void Ras::connect_in(int32_t j, void *peer_base, const MailboxLayout &pl, int32_t peer_send_offset)
+{
+    SCHWZ_REQUIRE(j >= 0 && j < (int32_t)nbr_in.size(), "in-neighbour index out of range");
+    const char *base = (const char *)peer_base;
+    in_send_host_[j] = (const double *)(base + pl.send_off) + peer_send_offset;
+    in_x_host_[j] = (const double *)(base + pl.x_off);
+    conv_peer_host_[nbr_in[j]] = (int32_t *)((char *)peer_base + pl.conv_off);
+    peer_tables_dirty_ = true;
+}
+
+void Ras::connect_conv(int32_t peer_rank, void *peer_base, const MailboxLayout &pl)
+{
+    SCHWZ_REQUIRE(peer_rank >= 0 && peer_rank < P, "subdomain id out of range");
+    conv_peer_host_[peer_rank] = (int32_t *)((char *)peer_base + pl.conv_off);
+    peer_tables_dirty_ = true;
+}
+
+void Ras::set_exchange_mode(int32_t mode)
+{
+    SCHWZ_REQUIRE(mode >= EXCHANGE_PUT_GATHERED && mode <= EXCHANGE_GET_ONE_BY_ONE,
+                  "unknown exchange mode");
+    exchange_mode = mode;
 }
 
 void Ras::upload_peer_tables()
@@ -337,8 +411,22 @@ void Ras::upload_peer_tables()
                                    cudaMemcpyHostToDevice, ctx.stream));
         SCHWZ_CUDA(cudaMemcpyAsync(out_conv_dev_, out_conv_host_.data(), no * sizeof(void *),
                                    cudaMemcpyHostToDevice, ctx.stream));
-        SCHWZ_CUDA(cudaStreamSynchronize(ctx.stream));
+        SCHWZ_CUDA(cudaMemcpyAsync(out_x_dev_, out_x_host_.data(), no * sizeof(void *),
+                                   cudaMemcpyHostToDevice, ctx.stream));
+        SCHWZ_CUDA(cudaMemcpyAsync(send_seg_dev_, send_seg_host_.data(), no * sizeof(void *),
+                                   cudaMemcpyHostToDevice, ctx.stream));
     }
+    const size_t ni = nbr_in.size();
+    ctx.use();
+    if (ni) {
+        SCHWZ_CUDA(cudaMemcpyAsync(in_send_dev_, in_send_host_.data(), ni * sizeof(void *),
+                                   cudaMemcpyHostToDevice, ctx.stream));
+        SCHWZ_CUDA(cudaMemcpyAsync(in_x_dev_, in_x_host_.data(), ni * sizeof(void *),
+                                   cudaMemcpyHostToDevice, ctx.stream));
+    }
+    SCHWZ_CUDA(cudaMemcpyAsync(conv_peer_dev_, conv_peer_host_.data(), (size_t)P * sizeof(void *),
+                               cudaMemcpyHostToDevice, ctx.stream));
+    SCHWZ_CUDA(cudaStreamSynchronize(ctx.stream));
     peer_tables_dirty_ = false;
 }
 
@@ -349,13 +437,22 @@ void Ras::exchange_push(int32_t iter)
 {
     upload_peer_tables();
     const int32_t no = (int32_t)nbr_out.size();
-    if (no > 0) {
+    if (no > 0 && exchange_mode == EXCHANGE_PUT_GATHERED) {
         // epochs count exchanges over the lifetime of the subdomain, so the
         // loop may be entered repeatedly (warm-up + timed runs)
         ++push_epoch_;
         launch_halo_pack_push(ctx, no, out_off_, out_total_, out_src_, x,
                               out_dst_dev_[push_epoch_ & 1], out_flag_dev_,
                               (unsigned long long)push_epoch_, nullptr);
+    } else if (no > 0 && exchange_mode == EXCHANGE_GET_GATHERED) {
+        // pack_buffer into my own send buffer; the receivers come and get it (:807-818)
+        launch_halo_pack_push(ctx, no, out_off_, out_total_, out_src_, x, send_seg_dev_, nullptr, 0,
+                              nullptr);
+    } else if (no > 0 && exchange_mode == EXCHANGE_PUT_ONE_BY_ONE) {
+        for (size_t j = 0; j < nbr_out.size(); ++j)
+            SCHWZ_REQUIRE(out_x_host_[j] != nullptr, "out-neighbour not connected");
+        launch_halo_put_elements(ctx, no, out_off_, out_total_, out_src_, out_remote_slot_, x,
+                                 out_x_dev_);
     }
     SCHWZ_CUDA(cudaEventRecord(ev_pushed, ctx.stream));
     last_push_iter = iter;
@@ -373,6 +470,18 @@ void Ras::exchange_unpack(int32_t iter, bool wait_flags)
 {
     const int32_t ni = (int32_t)nbr_in.size();
     if (ni == 0) return;
+    if (exchange_mode != EXCHANGE_PUT_GATHERED) {
+        SCHWZ_REQUIRE(!wait_flags, "only the Put-gathered exchange has a synchronous mode");
+        upload_peer_tables();
+        if (exchange_mode == EXCHANGE_PUT_ONE_BY_ONE) return;   // the Put was the update
+        const bool gathered = exchange_mode == EXCHANGE_GET_GATHERED;
+        for (int32_t j = 0; j < ni; ++j)
+            SCHWZ_REQUIRE((gathered ? in_send_host_[j] : in_x_host_[j]) != nullptr,
+                          "in-neighbour not connected (Get variants need connect_in)");
+        launch_halo_pull(ctx, ni, in_off_, in_total_, in_dst_, gathered ? nullptr : in_remote_idx_,
+                         gathered ? in_send_dev_ : in_x_dev_, x);
+        return;
+    }
     ++unpack_epoch_;
     const double *recv = (const double *)(mailbox + (unpack_epoch_ & 1) * mbox.recv_stride);
     const unsigned long long *flags =
@@ -447,6 +556,15 @@ void Ras::conv_forward(int32_t converged_all_local)
                         (int32_t)nbr_out.size(), out_conv_dev_, num_converged_dev);
 }
 
+void Ras::conv_tree(int32_t converged_all_local)
+{
+    upload_peer_tables();
+    if (rank > 0) SCHWZ_REQUIRE(conv_peer_host_[(rank - 1) / 2] != nullptr, "tree parent not connected");
+    for (int32_t p = 2 * rank + 1; p <= 2 * rank + 2; ++p)
+        if (p < P) SCHWZ_REQUIRE(conv_peer_host_[p] != nullptr, "tree child not connected");
+    launch_conv_tree(ctx, P, rank, converged_all_local, conv(), conv_peer_dev_, num_converged_dev);
+}
+
 // =============================================================================
 // The outer loop over the subdomains of this process.  One host thread drives
 // all local subdomains stage by stage; every stage is asynchronous on the
@@ -478,6 +596,9 @@ void ras_run(std::vector<Ras *> &subs, const LoopOptions &o, LoopResult &res,
     // map rank -> local subdomain (for same-process event waits)
     std::vector<Ras *> by_rank(P, nullptr);
     for (Ras *r : subs) by_rank[r->rank] = r;
+    SCHWZ_REQUIRE(o.enable_onesided || o.exchange_mode == EXCHANGE_PUT_GATHERED,
+                  "Get / one-by-one exchanges exist in one-sided mode only");
+    for (Ras *r : subs) r->set_exchange_mode(o.enable_onesided ? o.exchange_mode : EXCHANGE_PUT_GATHERED);
     for (Ras *r : subs) r->ctx.sync();
 
     auto t0 = std::chrono::steady_clock::now();
@@ -579,7 +700,8 @@ void ras_run(std::vector<Ras *> &subs, const LoopOptions &o, LoopResult &res,
                 if (r->finished) continue;
                 if (!(tol > 0.0 && iter_cond)) continue;
                 const int cal = (r->resnorm / r->resnorm0 <= tol) ? 1 : 0;
-                r->conv_forward(cal);
+                if (o.conv_tree) r->conv_tree(cal);
+                else r->conv_forward(cal);
                 r->ctx.use();
                 SCHWZ_CUDA(cudaMemcpyAsync(&counts[i], r->num_converged_dev, sizeof(int32_t),
                                            cudaMemcpyDeviceToHost, r->ctx.stream));

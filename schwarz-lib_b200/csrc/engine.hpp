@@ -112,8 +112,21 @@ struct MailboxLayout {
     int64_t flags_off = 0;     // n_in epoch words (u64)
     int64_t conv_off = 0;      // P convergence flags (i32)
     int64_t err_off = 0;       // 1 i32 error word
+    int64_t send_off = 0;      // send buffer (out_total doubles): what Get-gathered peers read
+    int64_t slots_off = 0;     // in_total i32: compact slot of every received element in x
+    int64_t x_off = 0;         // x itself (local_size_x + n_halo doubles): one-by-one Put / Get
     int64_t bytes = 0;
-    static MailboxLayout make(int64_t in_total, int32_t n_in, int32_t P);
+    static MailboxLayout make(int64_t in_total, int32_t n_in, int32_t P, int64_t out_total,
+                              int64_t x_len);
+};
+
+// How the halo values travel (Settings::comm_settings of the reference:
+// enable_put / enable_get x enable_one_by_one, restricted_schwarz.cpp:753-851).
+enum ExchangeMode {
+    EXCHANGE_PUT_GATHERED = 0,     // pack + peer stores into the neighbour's receive buffer, unpack
+    EXCHANGE_GET_GATHERED = 1,     // pack into the own send buffer; the receiver pulls + scatters
+    EXCHANGE_PUT_ONE_BY_ONE = 2,   // element-wise peer stores straight into the neighbour's x
+    EXCHANGE_GET_ONE_BY_ONE = 3    // element-wise peer loads straight from the neighbour's x
 };
 
 // One subdomain.  Vector layout in HBM (compact numbering = g2l - 1 of the
@@ -130,6 +143,14 @@ public:
                      const int32_t *perm);
     void connect(int32_t j_out, void *peer_base, const MailboxLayout &peer_layout,
                  int32_t peer_recv_offset, int32_t peer_flag_slot, bool same_process);
+    // in-neighbour j_in (Get variants): its mailbox and the offset of my block inside its
+    // send buffer (= get_displacements[neighbour], restricted_schwarz.cpp:642-658)
+    void connect_in(int32_t j_in, void *peer_base, const MailboxLayout &peer_layout,
+                    int32_t peer_send_offset);
+    // any subdomain's convergence words (the tree's parent / children need not be halo
+    // neighbours)
+    void connect_conv(int32_t peer_rank, void *peer_base, const MailboxLayout &peer_layout);
+    void set_exchange_mode(int32_t mode);
 
     // stages of SchwarzBase::run's loop body (source/schwarz_base.cpp:387-452)
     void exchange_push(int32_t iter);
@@ -178,10 +199,23 @@ public:
     int32_t *conv() const { return (int32_t *)(mailbox + mbox.conv_off); }
     int32_t *err_word() const { return (int32_t *)(mailbox + mbox.err_off); }
     void conv_forward(int32_t converged_all_local);
+    void conv_tree(int32_t converged_all_local);
+    int32_t exchange_mode = EXCHANGE_PUT_GATHERED;
 
 private:
     int32_t in_total_ = 0, out_total_ = 0;
     int32_t *in_dst_ = nullptr, *out_src_ = nullptr, *out_off_ = nullptr;
+    // Get / one-by-one variants
+    int32_t *in_off_ = nullptr;            // prefix sums of the in-list lengths
+    int32_t *in_remote_idx_ = nullptr;     // position of every in-element inside its owner's x
+    int32_t *out_remote_slot_ = nullptr;   // slot of every out-element inside the receiver's x
+    std::vector<int32_t> in_off_host_, out_off_host_;
+    std::vector<const double *> in_send_host_, in_x_host_;   // per in-neighbour
+    std::vector<double *> out_x_host_, send_seg_host_;       // per out-neighbour
+    const double **in_send_dev_ = nullptr, **in_x_dev_ = nullptr;
+    double **out_x_dev_ = nullptr, **send_seg_dev_ = nullptr;
+    std::vector<int32_t *> conv_peer_host_;                  // per subdomain id
+    int32_t **conv_peer_dev_ = nullptr;
     std::vector<double *> out_dst_host_[2];
     std::vector<unsigned long long *> out_flag_host_;
     std::vector<int32_t *> out_conv_host_;
@@ -201,6 +235,8 @@ struct LoopOptions {
     int32_t num_subdomains = 1, max_iters = 100;
     double tolerance = 1e-6;
     int32_t enable_onesided = 0, enable_global_check = 0, conv_decentralized = 0, iter_offset = 0;
+    // one-sided only: ExchangeMode, and 1 = centralised tree instead of flag flooding
+    int32_t exchange_mode = 0, conv_tree = 0;
     Comm *comm = nullptr;
 };
 struct LoopResult {

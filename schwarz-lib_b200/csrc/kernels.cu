@@ -924,6 +924,86 @@ void launch_halo_unpack(const Ctx &ctx, int32_t nseg, int32_t total, const int32
     count_launch();
 }
 
+// -----------------------------------------------------------------------------
+// The other three one-sided exchange variants of the reference
+// (restricted_schwarz.cpp:753-851, comm_helpers.hpp:58-89):
+//   * Put one-by-one: every element is stored straight into the neighbour's x
+//     at the slot the neighbour keeps it in (no buffers, no unpack) — MPI_Put
+//     per element on window_x becomes one peer store per element;
+//   * Get gathered:   the owner packs into its own send buffer, the receiver
+//     pulls its block out of it over NVLink and scatters in the same kernel
+//     (MPI_Get on window_send_buffer + unpack_buffer);
+//   * Get one-by-one: the receiver reads the owner's x directly (MPI_Get per
+//     element on window_x).
+// All three are asynchronous by construction: whatever the peer holds at that
+// moment is what travels.
+// -----------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock)
+    halo_put_elements_kernel(int32_t nseg, const int32_t *__restrict__ seg_off, int32_t total,
+                             const int32_t *__restrict__ src_idx,
+                             const int32_t *__restrict__ remote_slot, const double *__restrict__ x,
+                             double *const *__restrict__ peer_x)
+{
+    __shared__ int32_t s_off[kMaxSeg + 1];
+    __shared__ double *s_dst[kMaxSeg];
+    if (threadIdx.x <= nseg) s_off[threadIdx.x] = seg_off[threadIdx.x];
+    if (threadIdx.x < nseg) s_dst[threadIdx.x] = peer_x[threadIdx.x];
+    __syncthreads();
+    for (int32_t e = blockIdx.x * kBlock + threadIdx.x; e < total; e += gridDim.x * kBlock) {
+        int s = 0;
+        while (e >= s_off[s + 1]) ++s;
+        s_dst[s][remote_slot[e]] = x[src_idx[e]];
+    }
+    __threadfence_system();
+}
+
+void launch_halo_put_elements(const Ctx &ctx, int32_t nseg, const int32_t *seg_off_dev,
+                              int32_t total, const int32_t *src_idx, const int32_t *remote_slot,
+                              const double *x, double *const *peer_x)
+{
+    if (nseg <= 0 || total <= 0) return;
+    SCHWZ_REQUIRE(nseg <= kMaxSeg, "too many out-neighbours for one put launch");
+    ctx.use();
+    int grid = std::max(1, std::min((total + kBlock - 1) / kBlock, kVecGrid));
+    halo_put_elements_kernel<<<grid, kBlock, 0, ctx.stream>>>(nseg, seg_off_dev, total, src_idx,
+                                                              remote_slot, x, peer_x);
+    SCHWZ_CUDA(cudaGetLastError());
+    count_launch();
+}
+
+// x[dst_idx[e]] = src[s][ src_idx ? src_idx[e] : e - seg_off[s] ]  (peer loads)
+__global__ void __launch_bounds__(kBlock)
+    halo_pull_kernel(int32_t nseg, const int32_t *__restrict__ seg_off, int32_t total,
+                     const int32_t *__restrict__ dst_idx, const int32_t *__restrict__ src_idx,
+                     const double *const *__restrict__ src_ptrs, double *__restrict__ x)
+{
+    __shared__ int32_t s_off[kMaxSeg + 1];
+    __shared__ const double *s_src[kMaxSeg];
+    if (threadIdx.x <= nseg) s_off[threadIdx.x] = seg_off[threadIdx.x];
+    if (threadIdx.x < nseg) s_src[threadIdx.x] = src_ptrs[threadIdx.x];
+    __syncthreads();
+    for (int32_t e = blockIdx.x * kBlock + threadIdx.x; e < total; e += gridDim.x * kBlock) {
+        int s = 0;
+        while (e >= s_off[s + 1]) ++s;
+        const volatile double *src = s_src[s];   // peers write it: never cache in L1
+        x[dst_idx[e]] = src[src_idx != nullptr ? src_idx[e] : e - s_off[s]];
+    }
+}
+
+void launch_halo_pull(const Ctx &ctx, int32_t nseg, const int32_t *seg_off_dev, int32_t total,
+                      const int32_t *dst_idx, const int32_t *src_idx,
+                      const double *const *src_ptrs, double *x)
+{
+    if (nseg <= 0 || total <= 0) return;
+    SCHWZ_REQUIRE(nseg <= kMaxSeg, "too many in-neighbours for one pull launch");
+    ctx.use();
+    int grid = std::max(1, std::min((total + kBlock - 1) / kBlock, kVecGrid));
+    halo_pull_kernel<<<grid, kBlock, 0, ctx.stream>>>(nseg, seg_off_dev, total, dst_idx, src_idx,
+                                                      src_ptrs, x);
+    SCHWZ_CUDA(cudaGetLastError());
+    count_launch();
+}
+
 // =============================================================================
 // Decentralised convergence flags, include/conv_tools.hpp:248-274:
 //   if converged_all_local: conv[me] = 1 (sticky)
@@ -963,6 +1043,52 @@ void launch_conv_forward(const Ctx &ctx, int32_t P, int32_t me, int32_t converge
     ctx.use();
     conv_forward_kernel<<<1, 128, 0, ctx.stream>>>(P, me, converged_all_local, conv, conv_sent,
                                                    n_out, peer_conv, num_converged);
+    SCHWZ_CUDA(cudaGetLastError());
+    count_launch();
+}
+
+// =============================================================================
+// Centralised binary-tree convergence (Yamazaki et al. 2019), restated from
+// include/conv_tools.hpp:147-209 on the same peer-visible conv words:
+//   conv[0], conv[1] : "child 0 / child 1 has pushed up" (conv[0] == 2 once I pushed)
+//   conv[2]          : "the root has seen everybody" (pushed down)
+// peer_conv[q] = conv array of subdomain q (null when q is not connected).
+// =============================================================================
+__global__ void conv_tree_kernel(int32_t P, int32_t me, int32_t converged_all_local, int32_t *conv,
+                                 int32_t *const *peer_conv, int32_t *num_converged)
+{
+    if (threadIdx.x != 0) return;
+    const int c0 = ld_relaxed_sys_i32(conv + 0);
+    const int c1 = ld_relaxed_sys_i32(conv + 1);
+    if (((c0 == 1 && c1 == 1) || (c0 == 1 && me == P / 2 - 1) || (me >= P / 2 && c0 != 2)) &&
+        converged_all_local > 0) {
+        if (me == 0) {
+            st_relaxed_sys_i32(conv + 2, 1);
+        } else {
+            const int parent = (me - 1) / 2;
+            const int id = (me % 2 == 0) ? 1 : 0;
+            st_relaxed_sys_i32(peer_conv[parent] + id, 1);
+            __threadfence_system();
+        }
+        st_relaxed_sys_i32(conv + 0, 2);
+    }
+    if (ld_relaxed_sys_i32(conv + 2) == 1) {
+        for (int p = 2 * me + 1; p <= 2 * me + 2; ++p)
+            if (p < P) st_relaxed_sys_i32(peer_conv[p] + 2, 1);
+        __threadfence_system();
+        st_relaxed_sys_i32(conv + 1, ld_relaxed_sys_i32(conv + 1) + 1);
+        *num_converged = P;
+    } else {
+        *num_converged = 0;
+    }
+}
+
+void launch_conv_tree(const Ctx &ctx, int32_t P, int32_t me, int32_t converged_all_local,
+                      int32_t *conv, int32_t *const *peer_conv, int32_t *num_converged)
+{
+    ctx.use();
+    conv_tree_kernel<<<1, 32, 0, ctx.stream>>>(P, me, converged_all_local, conv, peer_conv,
+                                               num_converged);
     SCHWZ_CUDA(cudaGetLastError());
     count_launch();
 }

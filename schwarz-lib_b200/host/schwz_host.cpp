@@ -344,10 +344,13 @@ void Solve<V, I, M>::check_global_convergence(
     if (settings.comm_settings.enable_onesided) {
         if (settings.convergence_settings.enable_decentralized_leader_election ||
             settings.convergence_settings.enable_global_simple_tree) {
-            // flags live in the peer-visible mailboxes; the tree variant of the
-            // reference is served by the same flag flooding
+            // flags live in the peer-visible mailboxes: flooding along the halo graph
+            // (conv_tools.hpp:248-274) or the binary tree (conv_tools.hpp:147-209)
             int32_t n = 0;
-            B200_CHECK(schwz_b200_ras_conv_set_local(solve_dev_->ras, converged_all_local));
+            if (settings.convergence_settings.enable_global_simple_tree)
+                B200_CHECK(schwz_b200_ras_conv_tree(solve_dev_->ras, converged_all_local));
+            else
+                B200_CHECK(schwz_b200_ras_conv_set_local(solve_dev_->ras, converged_all_local));
             B200_CHECK(schwz_b200_ras_conv_count(solve_dev_->ras, &n));
             num_converged_procs = n;
         } else {
@@ -851,8 +854,13 @@ void SolverRAS<V, I, M>::exchange_boundary(const Settings &settings, const Metad
     if (metadata.num_subdomains < 2) return;
     if (settings.comm_settings.enable_onesided) {
         if (metadata.iter_count == 0) return;   // :725
-        // push into the neighbours' buffers, then unpack whatever mine holds —
-        // no synchronisation with the neighbours (one-sided semantics)
+        // push into the neighbours' buffers (or pack for them to pull), then unpack
+        // whatever mine holds (or pull) — no synchronisation with the neighbours
+        // (one-sided semantics).  enable_put/enable_get x enable_one_by_one (:753-851)
+        // select the data path.
+        const auto &c = settings.comm_settings;
+        const int32_t mode = (c.enable_put ? 0 : 1) + (c.enable_one_by_one ? 2 : 0);
+        B200_CHECK(schwz_b200_ras_set_exchange_mode(ras, mode));
         B200_CHECK(schwz_b200_ras_exchange_push(ras, metadata.iter_count));
         B200_CHECK(schwz_b200_ras_exchange_unpack(ras, metadata.iter_count, 0));
         return;

@@ -30,10 +30,12 @@ class RasOptions(C.Structure):
 
 class MailboxLayout(C.Structure):
     _fields_ = [("recv_stride", C.c_int64), ("flags_off", C.c_int64),
-                ("conv_off", C.c_int64), ("err_off", C.c_int64), ("bytes", C.c_int64)]
+                ("conv_off", C.c_int64), ("err_off", C.c_int64), ("send_off", C.c_int64),
+                ("slots_off", C.c_int64), ("x_off", C.c_int64), ("bytes", C.c_int64)]
 
     def as_tuple(self):
-        return (self.recv_stride, self.flags_off, self.conv_off, self.err_off, self.bytes)
+        return (self.recv_stride, self.flags_off, self.conv_off, self.err_off, self.send_off,
+                self.slots_off, self.x_off, self.bytes)
 
     @classmethod
     def from_tuple(cls, t):
@@ -44,7 +46,7 @@ class LoopOptions(C.Structure):
     _fields_ = [("num_subdomains", C.c_int32), ("max_iters", C.c_int32),
                 ("tolerance", C.c_double), ("enable_onesided", C.c_int32),
                 ("enable_global_check", C.c_int32), ("conv_decentralized", C.c_int32),
-                ("iter_offset", C.c_int32), ("reserved", C.c_int32),
+                ("iter_offset", C.c_int32), ("exchange_mode", C.c_int32),
                 ("comm", C.c_void_p)]
 
 
@@ -561,6 +563,29 @@ class Ras:
                                            C.byref(peer_layout), C.c_int32(recv_off),
                                            C.c_int32(flag_slot), C.c_int32(int(same_process))))
 
+    def connect_in(self, j_in, peer_base, peer_layout, send_off):
+        _chk(load().schwz_b200_ras_connect_in(self.h, C.c_int32(j_in), peer_base,
+                                              C.byref(peer_layout), C.c_int32(send_off)))
+
+    def connect_conv(self, peer_rank, peer_base, peer_layout):
+        _chk(load().schwz_b200_ras_connect_conv(self.h, C.c_int32(peer_rank), peer_base,
+                                                C.byref(peer_layout)))
+
+    def set_exchange_mode(self, mode):
+        """EXCHANGE_MODES key or number (Settings::comm_settings put/get x one-by-one)."""
+        _chk(load().schwz_b200_ras_set_exchange_mode(self.h, C.c_int32(_exchange_mode(mode))))
+
+    def conv_tree(self, converged_all_local):
+        _chk(load().schwz_b200_ras_conv_tree(self.h, C.c_int32(int(converged_all_local))))
+
+    def conv_set_local(self, converged_all_local):
+        _chk(load().schwz_b200_ras_conv_set_local(self.h, C.c_int32(int(converged_all_local))))
+
+    def conv_count(self):
+        n = C.c_int32()
+        _chk(load().schwz_b200_ras_conv_count(self.h, C.byref(n)))
+        return int(n.value)
+
     # loop stages
     def exchange_push(self, it):
         _chk(load().schwz_b200_ras_exchange_push(self.h, C.c_int32(it)))
@@ -635,12 +660,24 @@ class Ras:
         return out.value
 
 
-def mailbox_layout(in_total, n_in, P):
+EXCHANGE_MODES = {"put": 0, "get": 1, "put-one-by-one": 2, "get-one-by-one": 3}
+
+
+def _exchange_mode(mode):
+    return EXCHANGE_MODES[mode] if isinstance(mode, str) else int(mode)
+
+
+def exchange_mode(remote_comm_type="put", enable_one_by_one=False):
+    """bench_ras flags --remote_comm_type / --enable_one_by_one -> exchange mode."""
+    return EXCHANGE_MODES[remote_comm_type + ("-one-by-one" if enable_one_by_one else "")]
+
+
+def mailbox_layout(in_total, n_in, P, out_total=0, x_len=0):
     """Layout of a subdomain's peer-visible mailbox from its index-set sizes
     (host only; the same function the device side uses)."""
     lay = MailboxLayout()
     _chk(load().schwz_b200_mailbox_layout(C.c_int64(in_total), C.c_int32(n_in), C.c_int32(P),
-                                          C.byref(lay)))
+                                          C.c_int64(out_total), C.c_int64(x_len), C.byref(lay)))
     return lay
 
 
@@ -673,13 +710,14 @@ def connect_local(subs, setup):
 
 def ras_run(subs, num_subdomains, max_iters, tolerance=1e-6, enable_onesided=False,
             enable_global_check=True, conv_decentralized=False, iter_offset=False, comm=None,
-            history=False):
+            history=False, exchange="put"):
     """The outer loop of SchwarzBase::run (source/schwarz_base.cpp:387-452) over
-    the subdomains of this process."""
+    the subdomains of this process.  One-sided runs: conv_decentralized selects the flag
+    flooding protocol (else the centralised tree), `exchange` one of EXCHANGE_MODES."""
     arr = (C.c_void_p * len(subs))(*[s.h for s in subs])
     o = LoopOptions(num_subdomains, max_iters, tolerance, int(enable_onesided),
-                    int(enable_global_check), int(conv_decentralized), int(iter_offset), 0,
-                    comm.h if comm is not None else None)
+                    int(enable_global_check), int(conv_decentralized), int(iter_offset),
+                    _exchange_mode(exchange), comm.h if comm is not None else None)
     res = LoopResult()
     hist = np.zeros((max_iters, len(subs))) if history else None
     _chk(load().schwz_b200_ras_run(arr, C.c_int32(len(subs)), C.byref(o), C.byref(res), _p(hist)))

@@ -1,0 +1,124 @@
+"""The four one-sided data paths of the reference (Settings::comm_settings enable_put /
+enable_get x enable_one_by_one, source/restricted_schwarz.cpp:753-851) and the centralised
+tree convergence protocol (include/conv_tools.hpp:147-209) on the GPU, through the C ABI.
+
+* data movement: with x[own] set to a known function of the global index, ONE exchange of
+  every variant must leave exactly the owners' values in every overlap / halo slot
+  (bit-exact: the exchange only moves doubles);
+* protocol: an asynchronous run of every variant stops by itself and meets the threshold the
+  oracle reaches (the north star's criterion for async mode).
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+MODES = ["put", "get", "put-one-by-one", "get-one-by-one"]
+
+
+@pytest.fixture(autouse=True)
+def _need_gpu(sz):
+    if sz.device_count() < 1:
+        pytest.skip("no CUDA device")
+
+
+def _build(sz, setup, P, **kw):
+    ctxs = [sz.Context(0) for _ in range(P)]
+    subs = [sz.Ras(ctxs[r], setup, r, **kw) for r in range(P)]
+    sz.connect_local(subs, setup)
+    return ctxs, subs
+
+
+def _close(ctxs, subs):
+    for s in subs:
+        s.close()
+    for c in ctxs:
+        c.close()
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("case", ["strips", "regular2d", "ani4_metis"])
+def test_one_exchange_moves_exactly_the_owners_values(sz, ani4, mode, case):
+    if case == "strips":
+        P, N = 4, 24 * 24
+        setup = sz.Setup(("laplacian2d", 24), P)
+    elif case == "regular2d":
+        P, N = 4, 16 * 16
+        setup = sz.Setup(("laplacian2d", 16), P, part=sz.partition_regular2d(N, P))
+    else:
+        P, N = 8, len(ani4[0]) - 1
+        setup = sz.Setup(ani4, P, part=sz.partition_metis(ani4[0], ani4[1], P))
+    ctxs, subs = _build(sz, setup, P)
+    f = lambda gid: np.sin(gid.astype(np.float64)) * 1e3 + gid      # noqa: E731
+    fr = setup.first_row()
+    for r, s in enumerate(subs):
+        s.set_exchange_mode(mode)
+        s.set_x_own(f(np.arange(fr[r], fr[r + 1])))
+    for s in subs:
+        s.exchange_push(1)
+    for s in subs:
+        s.sync()                      # every pack / put has landed
+    for s in subs:
+        s.exchange_unpack(1)
+    for r, s in enumerate(subs):
+        l2g = setup.l2g(r)
+        got = s.x()
+        # every slot whose owner is a neighbour now holds the owner's value; own slots unchanged
+        assert np.array_equal(got, f(l2g)), (mode, case, r)
+    _close(ctxs, subs)
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("conv", ["decentralized", "centralized-tree"])
+def test_async_run_stops_and_meets_the_threshold(sz, orc, mode, conv):
+    n, P, tol = 24, 4, 1e-6
+    mat = orc.laplacian2d(n)
+    ob = orc.Problem(*mat, P)
+    ob.configure(tolerance=tol, max_iters=4000, enable_onesided=True,
+                 remote_comm_type=mode.split("-")[0], enable_one_by_one=mode.endswith("one-by-one"),
+                 global_convergence_type=conv)
+    ob.run()
+    _, fro = ob.final_residual()
+    setup = sz.Setup(("laplacian2d", n), P)
+    ctxs, subs = _build(sz, setup, P)
+    out = sz.ras_run(subs, P, 4000, tolerance=tol, enable_onesided=True,
+                     conv_decentralized=(conv == "decentralized"), exchange=mode)
+    assert out["converged"] and out["iters"] < 4000
+    for s in subs:
+        s.set_exchange_mode("put")
+        s.exchange_push(0)
+    for s in subs:
+        s.sync()
+    for s in subs:
+        s.exchange_unpack(0)
+    rel = np.sqrt(sum(s.true_residual_sq() for s in subs)) / np.sqrt(n * n)
+    assert rel <= max(10 * fro["relative"], 50 * tol)
+    _close(ctxs, subs)
+
+
+def test_tree_protocol_step_by_step(sz):
+    """conv words after each call, P = 5 (ranks 2, 3, 4 are leaves, rank 1 has two children,
+    rank 0 has children 1 and 2): nothing is announced until every leaf has pushed up, then
+    the root's flag travels down one level per call."""
+    P = 5
+    setup = sz.Setup(("laplacian2d", 10), P)
+    ctxs, subs = _build(sz, setup, P)
+
+    def call(flags):
+        out = []
+        for s, f in zip(subs, flags):
+            s.conv_tree(f)
+        for s in subs:
+            out.append(s.conv_count())
+        return out
+
+    assert call([0, 0, 0, 0, 0]) == [0] * 5
+    assert call([1, 1, 0, 1, 1]) == [0] * 5          # leaf 2 missing: root cannot fire
+    # now everybody is locally converged: 2 pushes to 0; 1 (children pushed above) pushes to
+    # 0 in the same sweep because its conv[0], conv[1] were set by 3 and 4 one call earlier
+    got = call([1, 1, 1, 1, 1])
+    assert got[0] in (0, P)                            # root fires once both children are in
+    for _ in range(4):
+        got = call([1, 1, 1, 1, 1])
+    assert got == [P] * 5
+    _close(ctxs, subs)
