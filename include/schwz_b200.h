@@ -205,7 +205,8 @@ typedef struct {
     int32_t non_symmetric;     /* GMRES instead of CG            */
     int32_t restart_iter;
     int32_t overlap;
-    int32_t reserved;
+    int32_t use_mixed_precision; /* settings.use_mixed_precision, MixedValueType = float: halo
+                                  * values travel as floats (restricted_schwarz.cpp:483-603) */
 } schwz_ras_options;
 
 int schwz_b200_ras_create(schwz_ctx *ctx, schwz_setup *s, int32_t rank,

@@ -44,7 +44,7 @@ class OrcOptions(C.Structure):
         ("conv_decentralized", C.c_int32),
         ("enable_accumulate", C.c_int32),
         ("iter_offset", C.c_int32),
-        ("reserved", C.c_int32),
+        ("use_mixed_precision", C.c_int32),
     ]
 
 
@@ -285,7 +285,8 @@ class Problem:
                   remote_comm_type="get", enable_one_by_one=False,
                   enable_global_check=False,
                   global_convergence_type="centralized-tree",
-                  enable_accumulate=False, iter_offset=False, factor_perms=None):
+                  enable_accumulate=False, iter_offset=False, factor_perms=None,
+                  use_mixed_precision=False):
         o = OrcOptions()
         o.tolerance = tolerance
         o.local_tol = local_tol
@@ -302,6 +303,7 @@ class Problem:
         o.conv_decentralized = int(global_convergence_type == "decentralized")
         o.enable_accumulate = int(enable_accumulate)
         o.iter_offset = int(iter_offset)
+        o.use_mixed_precision = int(use_mixed_precision)
         perm_all = None
         if factor_perms is not None:
             perm_all = np.ascontiguousarray(np.concatenate(factor_perms), np.int32)

@@ -223,6 +223,7 @@ struct Options {
     int enable_accumulate = 0;
     int iter_offset = 0;            // enable_global_check_iter_offset
     int overlap = 2;                // settings.overlap (for update_boundary)
+    int use_mixed_precision = 0;    // settings.use_mixed_precision with MixedValueType = float
 };
 
 struct Rank {
@@ -873,8 +874,12 @@ void exchange_twosided(Problem &pb)
                 if (S.nbr_out[jj] == q) break;
                 off += S.put[jj].size();
             }
+            // use_mixed_precision (restricted_schwarz.cpp:898-903, 952-954): the values travel
+            // as MixedValueType (float mirrors of the send / receive buffers)
             for (size_t k = 0; k < R.get[j].size(); ++k)
-                R.recv_buf[num_get + k] = S.send_buf[off + k];
+                R.recv_buf[num_get + k] = pb.opt.use_mixed_precision
+                                              ? (double)(float)S.send_buf[off + k]
+                                              : S.send_buf[off + k];
             for (size_t k = 0; k < R.get[j].size(); ++k)
                 R.x[R.get[j][k]] = R.recv_buf[num_get + k];
             num_get += R.get[j].size();
@@ -908,7 +913,9 @@ void exchange_onesided_rank(Problem &pb, int p)
                     R.send_buf[num_put + k] = R.x[R.put[j][k]];  // pack_buffer
                 // transfer_buffer: MPI_Put at put_displacements[q]
                 for (size_t k = 0; k < R.put[j].size(); ++k)
-                    Q.recv_buf[R.put_disp[q] + k] = R.send_buf[num_put + k];
+                    Q.recv_buf[R.put_disp[q] + k] = o.use_mixed_precision
+                                                        ? (double)(float)R.send_buf[num_put + k]
+                                                        : R.send_buf[num_put + k];   // :769-787
                 num_put += R.put[j].size();
             }
             size_t num_get = 0;
@@ -939,7 +946,9 @@ void exchange_onesided_rank(Problem &pb, int p)
                 // reference tests global_put[p][0] here (:823-824, SURVEY
                 // Appendix D) — the oracle uses the in-list count.
                 for (size_t k = 0; k < R.get[j].size(); ++k)
-                    R.recv_buf[num_get + k] = Q.send_buf[R.get_disp[q] + k];
+                    R.recv_buf[num_get + k] = o.use_mixed_precision
+                                                  ? (double)(float)Q.send_buf[R.get_disp[q] + k]
+                                                  : Q.send_buf[R.get_disp[q] + k];   // :819-835
                 for (size_t k = 0; k < R.get[j].size(); ++k)
                     R.x[R.get[j][k]] = R.recv_buf[num_get + k];
                 num_get += R.get[j].size();
@@ -1470,7 +1479,7 @@ struct orc_options {
     int32_t max_iters, local_max_iters, non_symmetric, restart_iter,
         local_solver, enable_onesided, enable_put, enable_one_by_one,
         enable_global_check, conv_tree, conv_decentralized, enable_accumulate,
-        iter_offset, reserved;
+        iter_offset, use_mixed_precision;
 };
 
 void orc_set_rhs(void *h, const double *rhs)
@@ -1501,6 +1510,7 @@ int orc_configure(void *h, const orc_options *o, const idx *perm_all)
     d.conv_decentralized = o->conv_decentralized;
     d.enable_accumulate = o->enable_accumulate;
     d.iter_offset = o->iter_offset;
+    d.use_mixed_precision = o->use_mixed_precision;
     d.overlap = pb->overlap;
     setup_windows(*pb);
     setup_vectors(*pb);

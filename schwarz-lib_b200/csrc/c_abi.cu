@@ -565,6 +565,7 @@ int schwz_b200_ras_create(schwz_ctx *ctx, schwz_setup *s, int32_t rank, const do
     ro.non_symmetric = o->non_symmetric;
     ro.restart_iter = o->restart_iter;
     ro.overlap = o->overlap;
+    ro.use_mixed_precision = o->use_mixed_precision;
     auto *h = new schwz_ras();
     h->impl.reset(new Ras(ctx->impl, *s->impl, rank, rhs, ro));
     *out = h;

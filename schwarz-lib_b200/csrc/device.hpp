@@ -116,18 +116,18 @@ void launch_cg_xr_update(const Ctx &ctx, int64_t n, double *x, double *r, const 
 // halo
 void launch_halo_pack_push(const Ctx &ctx, int32_t nseg, const int32_t *seg_off_dev,
                            int32_t total, const int32_t *src_idx, const double *x,
-                           double *const *dst_ptrs, unsigned long long *const *flag_ptrs,
-                           unsigned long long epoch, const int32_t *stop);
+                           void *const *dst_ptrs, unsigned long long *const *flag_ptrs,
+                           unsigned long long epoch, const int32_t *stop, bool f32 = false);
 void launch_halo_unpack(const Ctx &ctx, int32_t nseg, int32_t total, const int32_t *dst_idx,
-                        const double *recv, double *x, const unsigned long long *flags,
-                        unsigned long long epoch, int32_t *error_flag);
+                        const void *recv, double *x, const unsigned long long *flags,
+                        unsigned long long epoch, int32_t *error_flag, bool f32 = false);
 
 void launch_halo_put_elements(const Ctx &ctx, int32_t nseg, const int32_t *seg_off_dev,
                               int32_t total, const int32_t *src_idx, const int32_t *remote_slot,
                               const double *x, double *const *peer_x);
 void launch_halo_pull(const Ctx &ctx, int32_t nseg, const int32_t *seg_off_dev, int32_t total,
                       const int32_t *dst_idx, const int32_t *src_idx,
-                      const double *const *src_ptrs, double *x);
+                      const void *const *src_ptrs, double *x, bool f32 = false);
 
 // convergence flags (include/conv_tools.hpp:248-274 on peer-mapped words)
 void launch_conv_forward(const Ctx &ctx, int32_t P, int32_t me, int32_t converged_all_local,

@@ -209,11 +209,11 @@ Ras::Ras(const Ctx &ctx_, Setup &setup, int32_t rank_, const double *host_rhs_gl
     out_x_host_.assign(no, nullptr);
     send_seg_host_.assign(no, nullptr);
     for (size_t j = 0; j < no; ++j)
-        send_seg_host_[j] = (double *)(mailbox + mbox.send_off) + out_off_host_[j];
-    in_send_dev_ = ctx.alloc_zero<const double *>(std::max<size_t>(ni, 1));
-    in_x_dev_ = ctx.alloc_zero<const double *>(std::max<size_t>(ni, 1));
+        send_seg_host_[j] = mailbox + mbox.send_off + wire_size() * (size_t)out_off_host_[j];
+    in_send_dev_ = ctx.alloc_zero<const void *>(std::max<size_t>(ni, 1));
+    in_x_dev_ = ctx.alloc_zero<const void *>(std::max<size_t>(ni, 1));
     out_x_dev_ = ctx.alloc_zero<double *>(std::max<size_t>(no, 1));
-    send_seg_dev_ = ctx.alloc_zero<double *>(std::max<size_t>(no, 1));
+    send_seg_dev_ = ctx.alloc_zero<void *>(std::max<size_t>(no, 1));
     conv_peer_host_.assign((size_t)P, nullptr);
     conv_peer_host_[rank] = conv();
     conv_peer_dev_ = ctx.alloc_zero<int32_t *>((size_t)P);
@@ -221,7 +221,7 @@ Ras::Ras(const Ctx &ctx_, Setup &setup, int32_t rank_, const double *host_rhs_gl
     out_flag_host_.assign(no, nullptr);
     out_conv_host_.assign(no, nullptr);
     out_same_process_.assign(no, 1);
-    for (int b = 0; b < 2; ++b) out_dst_dev_[b] = ctx.alloc_zero<double *>(std::max<size_t>(no, 1));
+    for (int b = 0; b < 2; ++b) out_dst_dev_[b] = ctx.alloc_zero<void *>(std::max<size_t>(no, 1));
     out_flag_dev_ = ctx.alloc_zero<unsigned long long *>(std::max<size_t>(no, 1));
     out_conv_dev_ = ctx.alloc_zero<int32_t *>(std::max<size_t>(no, 1));
     SCHWZ_CUDA(cudaEventCreateWithFlags(&ev_pushed, cudaEventDisableTiming));
@@ -352,7 +352,7 @@ void Ras::connect(int32_t j, void *peer_base, const MailboxLayout &pl, int32_t p
     SCHWZ_REQUIRE(j >= 0 && j < (int32_t)nbr_out.size(), "out-neighbour index out of range");
     char *base = (char *)peer_base;
     for (int b = 0; b < 2; ++b)
-        out_dst_host_[b][j] = (double *)(base + b * pl.recv_stride) + peer_recv_offset;
+        out_dst_host_[b][j] = base + b * pl.recv_stride + wire_size() * (size_t)peer_recv_offset;
     out_flag_host_[j] = (unsigned long long *)(base + pl.flags_off) + peer_flag_slot;
     out_conv_host_[j] = (int32_t *)(base + pl.conv_off);
     out_same_process_[j] = same_process ? 1 : 0;
@@ -373,8 +373,8 @@ void Ras::connect_in(int32_t j, void *peer_base, const MailboxLayout &pl, int32_
 {
     SCHWZ_REQUIRE(j >= 0 && j < (int32_t)nbr_in.size(), "in-neighbour index out of range");
     const char *base = (const char *)peer_base;
-    in_send_host_[j] = (const double *)(base + pl.send_off) + peer_send_offset;
-    in_x_host_[j] = (const double *)(base + pl.x_off);
+    in_send_host_[j] = base + pl.send_off + wire_size() * (size_t)peer_send_offset;
+    in_x_host_[j] = base + pl.x_off;
     conv_peer_host_[nbr_in[j]] = (int32_t *)((char *)peer_base + pl.conv_off);
     peer_tables_dirty_ = true;
 }
@@ -443,11 +443,11 @@ void Ras::exchange_push(int32_t iter)
         ++push_epoch_;
         launch_halo_pack_push(ctx, no, out_off_, out_total_, out_src_, x,
                               out_dst_dev_[push_epoch_ & 1], out_flag_dev_,
-                              (unsigned long long)push_epoch_, nullptr);
+                              (unsigned long long)push_epoch_, nullptr, opt.use_mixed_precision != 0);
     } else if (no > 0 && exchange_mode == EXCHANGE_GET_GATHERED) {
         // pack_buffer into my own send buffer; the receivers come and get it (:807-818)
         launch_halo_pack_push(ctx, no, out_off_, out_total_, out_src_, x, send_seg_dev_, nullptr, 0,
-                              nullptr);
+                              nullptr, opt.use_mixed_precision != 0);
     } else if (no > 0 && exchange_mode == EXCHANGE_PUT_ONE_BY_ONE) {
         for (size_t j = 0; j < nbr_out.size(); ++j)
             SCHWZ_REQUIRE(out_x_host_[j] != nullptr, "out-neighbour not connected");
@@ -478,16 +478,18 @@ void Ras::exchange_unpack(int32_t iter, bool wait_flags)
         for (int32_t j = 0; j < ni; ++j)
             SCHWZ_REQUIRE((gathered ? in_send_host_[j] : in_x_host_[j]) != nullptr,
                           "in-neighbour not connected (Get variants need connect_in)");
+        // one-by-one moves ValueType elements of x itself: no float mirror (comm_helpers.hpp:58-89)
         launch_halo_pull(ctx, ni, in_off_, in_total_, in_dst_, gathered ? nullptr : in_remote_idx_,
-                         gathered ? in_send_dev_ : in_x_dev_, x);
+                         gathered ? in_send_dev_ : in_x_dev_, x,
+                         gathered && opt.use_mixed_precision != 0);
         return;
     }
     ++unpack_epoch_;
-    const double *recv = (const double *)(mailbox + (unpack_epoch_ & 1) * mbox.recv_stride);
+    const void *recv = mailbox + (unpack_epoch_ & 1) * mbox.recv_stride;
     const unsigned long long *flags =
         wait_flags ? (const unsigned long long *)(mailbox + mbox.flags_off) : nullptr;
     launch_halo_unpack(ctx, ni, in_total_, in_dst_, recv, x, flags,
-                       (unsigned long long)unpack_epoch_, err_word());
+                       (unsigned long long)unpack_epoch_, err_word(), opt.use_mixed_precision != 0);
 }
 
 // A9: local_solution = local_rhs - I * x  (source/restricted_schwarz.cpp:992-1017)

@@ -104,6 +104,9 @@ struct RasOptions {
     double tolerance = 1e-6, local_tol = 1e-12;
     int32_t local_max_iters = -1, local_solver = 2, non_symmetric = 0, restart_iter = 1,
             overlap = 2;
+    // settings.use_mixed_precision with MixedValueType = float: halo values travel as floats
+    // in the gathered exchanges (restricted_schwarz.cpp:483-603, 769-787, 898-903)
+    int32_t use_mixed_precision = 0;
 };
 
 // Layout of the peer-visible mailbox of a subdomain (byte offsets from base).
@@ -210,17 +213,20 @@ private:
     int32_t *in_remote_idx_ = nullptr;     // position of every in-element inside its owner's x
     int32_t *out_remote_slot_ = nullptr;   // slot of every out-element inside the receiver's x
     std::vector<int32_t> in_off_host_, out_off_host_;
-    std::vector<const double *> in_send_host_, in_x_host_;   // per in-neighbour
-    std::vector<double *> out_x_host_, send_seg_host_;       // per out-neighbour
-    const double **in_send_dev_ = nullptr, **in_x_dev_ = nullptr;
-    double **out_x_dev_ = nullptr, **send_seg_dev_ = nullptr;
+    std::vector<const void *> in_send_host_, in_x_host_;     // per in-neighbour
+    std::vector<double *> out_x_host_;                       // per out-neighbour
+    std::vector<void *> send_seg_host_;
+    const void **in_send_dev_ = nullptr, **in_x_dev_ = nullptr;
+    double **out_x_dev_ = nullptr;
+    void **send_seg_dev_ = nullptr;
+    size_t wire_size() const { return opt.use_mixed_precision ? sizeof(float) : sizeof(double); }
     std::vector<int32_t *> conv_peer_host_;                  // per subdomain id
     int32_t **conv_peer_dev_ = nullptr;
-    std::vector<double *> out_dst_host_[2];
+    std::vector<void *> out_dst_host_[2];
     std::vector<unsigned long long *> out_flag_host_;
     std::vector<int32_t *> out_conv_host_;
     std::vector<char> out_same_process_;
-    double **out_dst_dev_[2] = {nullptr, nullptr};
+    void **out_dst_dev_[2] = {nullptr, nullptr};
     unsigned long long **out_flag_dev_ = nullptr;
     int32_t **out_conv_dev_ = nullptr;
     bool any_remote_ = false;

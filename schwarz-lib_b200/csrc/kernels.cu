@@ -489,8 +489,6 @@ void launch_spmv(const Ctx &ctx, const DeviceCsr &A, double alpha, const double 
             SCHWZ_CUDA(cudaMemsetAsync(result, 0, sizeof(double), ctx.stream));
         return;
     }
-    SCHWZ_REQUIRE(A.nblocks <= kMaxPartials || epi == EPI_NONE,
-                  "matrix too large for the fused reduction scratch");
     ctx.use();
     if (!A.has_long_row && !g_force_simple_spmv) {
         switch (epi) {
@@ -503,6 +501,9 @@ void launch_spmv(const Ctx &ctx, const DeviceCsr &A, double alpha, const double 
         count_launch();
         return;
     }
+    // one partial per tile here (the persistent kernel above needs one per resident CTA only)
+    SCHWZ_REQUIRE(A.nblocks <= kMaxPartials || epi == EPI_NONE,
+                  "matrix too large for the fused reduction scratch of the one-shot SpMV");
     dim3 grid(A.nblocks), block(kBlock);
 #define SCHWZ_SPMV_CASE(E)                                                                   \
     csr_spmv_stream_kernel<E><<<grid, block, 0, ctx.stream>>>(                               \
@@ -839,23 +840,27 @@ void launch_cg_xr_update(const Ctx &ctx, int64_t n, double *x, double *r, const 
 // =============================================================================
 constexpr int kMaxSeg = 64;
 
+// T = payload type on the wire: double, or float for use_mixed_precision (the float
+// mirrors mixedt_send_buffer / mixedt_recv_buffer of restricted_schwarz.cpp:483-603, 769-787,
+// 898-903: values are rounded to MixedValueType by the sender, widened by the receiver).
+template <typename T>
 __global__ void __launch_bounds__(kBlock)
     halo_pack_push_kernel(int32_t nseg, const int32_t *__restrict__ seg_off, int32_t total,
                           const int32_t *__restrict__ src_idx, const double *__restrict__ x,
-                          double *const *__restrict__ dst_ptrs,
+                          void *const *__restrict__ dst_ptrs,
                           unsigned long long *const *__restrict__ flag_ptrs,
                           unsigned long long epoch, unsigned int *ticket, const int32_t *stop)
 {
     __shared__ int32_t s_off[kMaxSeg + 1];
-    __shared__ double *s_dst[kMaxSeg];
+    __shared__ T *s_dst[kMaxSeg];
     if (stop != nullptr && *stop != 0) return;
     if (threadIdx.x <= nseg) s_off[threadIdx.x] = seg_off[threadIdx.x];
-    if (threadIdx.x < nseg) s_dst[threadIdx.x] = dst_ptrs[threadIdx.x];
+    if (threadIdx.x < nseg) s_dst[threadIdx.x] = (T *)dst_ptrs[threadIdx.x];
     __syncthreads();
     for (int32_t e = blockIdx.x * kBlock + threadIdx.x; e < total; e += gridDim.x * kBlock) {
         int s = 0;
         while (e >= s_off[s + 1]) ++s;
-        s_dst[s][e - s_off[s]] = x[src_idx[e]];
+        s_dst[s][e - s_off[s]] = (T)x[src_idx[e]];
     }
     if (flag_ptrs != nullptr) {
         __threadfence_system();   // my peer stores are visible system-wide
@@ -867,15 +872,19 @@ __global__ void __launch_bounds__(kBlock)
 
 void launch_halo_pack_push(const Ctx &ctx, int32_t nseg, const int32_t *seg_off_dev,
                            int32_t total, const int32_t *src_idx, const double *x,
-                           double *const *dst_ptrs, unsigned long long *const *flag_ptrs,
-                           unsigned long long epoch, const int32_t *stop)
+                           void *const *dst_ptrs, unsigned long long *const *flag_ptrs,
+                           unsigned long long epoch, const int32_t *stop, bool f32)
 {
     if (nseg <= 0) return;
     SCHWZ_REQUIRE(nseg <= kMaxSeg, "too many out-neighbours for one push launch");
     ctx.use();
     int grid = std::max(1, std::min((total + kBlock - 1) / kBlock, kVecGrid));
-    halo_pack_push_kernel<<<grid, kBlock, 0, ctx.stream>>>(
-        nseg, seg_off_dev, total, src_idx, x, dst_ptrs, flag_ptrs, epoch, ctx.tickets + 3, stop);
+    if (f32)
+        halo_pack_push_kernel<float><<<grid, kBlock, 0, ctx.stream>>>(
+            nseg, seg_off_dev, total, src_idx, x, dst_ptrs, flag_ptrs, epoch, ctx.tickets + 3, stop);
+    else
+        halo_pack_push_kernel<double><<<grid, kBlock, 0, ctx.stream>>>(
+            nseg, seg_off_dev, total, src_idx, x, dst_ptrs, flag_ptrs, epoch, ctx.tickets + 3, stop);
     SCHWZ_CUDA(cudaGetLastError());
     count_launch();
 }
@@ -886,9 +895,10 @@ void launch_halo_pack_push(const Ctx &ctx, int32_t nseg, const int32_t *seg_off_
 // (synchronous semantics across processes); without, it scatters whatever the
 // buffer holds (asynchronous semantics).  The wait is bounded so a lost peer
 // cannot hang the GPU; on expiry error_flag is raised.
+template <typename T>
 __global__ void __launch_bounds__(kBlock)
     halo_unpack_kernel(int32_t nseg, int32_t total, const int32_t *__restrict__ dst_idx,
-                       const double *recv, double *__restrict__ x,
+                       const void *recv, double *__restrict__ x,
                        const unsigned long long *flags, unsigned long long epoch,
                        int32_t *error_flag)
 {
@@ -905,21 +915,25 @@ __global__ void __launch_bounds__(kBlock)
         }
         __syncthreads();
     }
-    const volatile double *rv = recv;   // written by peers: never cache in L1
+    const volatile T *rv = (const volatile T *)recv;   // written by peers: never cache in L1
     for (int32_t e = blockIdx.x * kBlock + threadIdx.x; e < total; e += gridDim.x * kBlock)
-        x[dst_idx[e]] = rv[e];
+        x[dst_idx[e]] = (double)rv[e];
 }
 
 void launch_halo_unpack(const Ctx &ctx, int32_t nseg, int32_t total, const int32_t *dst_idx,
-                        const double *recv, double *x, const unsigned long long *flags,
-                        unsigned long long epoch, int32_t *error_flag)
+                        const void *recv, double *x, const unsigned long long *flags,
+                        unsigned long long epoch, int32_t *error_flag, bool f32)
 {
     if (nseg <= 0 || total <= 0) return;
     SCHWZ_REQUIRE(nseg <= kBlock, "too many in-neighbours for one unpack launch");
     ctx.use();
     int grid = std::max(1, std::min((total + kBlock - 1) / kBlock, kVecGrid));
-    halo_unpack_kernel<<<grid, kBlock, 0, ctx.stream>>>(nseg, total, dst_idx, recv, x, flags,
-                                                        epoch, error_flag);
+    if (f32)
+        halo_unpack_kernel<float><<<grid, kBlock, 0, ctx.stream>>>(nseg, total, dst_idx, recv, x,
+                                                                   flags, epoch, error_flag);
+    else
+        halo_unpack_kernel<double><<<grid, kBlock, 0, ctx.stream>>>(nseg, total, dst_idx, recv, x,
+                                                                    flags, epoch, error_flag);
     SCHWZ_CUDA(cudaGetLastError());
     count_launch();
 }
@@ -972,34 +986,39 @@ void launch_halo_put_elements(const Ctx &ctx, int32_t nseg, const int32_t *seg_o
 }
 
 // x[dst_idx[e]] = src[s][ src_idx ? src_idx[e] : e - seg_off[s] ]  (peer loads)
+template <typename T>
 __global__ void __launch_bounds__(kBlock)
     halo_pull_kernel(int32_t nseg, const int32_t *__restrict__ seg_off, int32_t total,
                      const int32_t *__restrict__ dst_idx, const int32_t *__restrict__ src_idx,
-                     const double *const *__restrict__ src_ptrs, double *__restrict__ x)
+                     const void *const *__restrict__ src_ptrs, double *__restrict__ x)
 {
     __shared__ int32_t s_off[kMaxSeg + 1];
-    __shared__ const double *s_src[kMaxSeg];
+    __shared__ const T *s_src[kMaxSeg];
     if (threadIdx.x <= nseg) s_off[threadIdx.x] = seg_off[threadIdx.x];
-    if (threadIdx.x < nseg) s_src[threadIdx.x] = src_ptrs[threadIdx.x];
+    if (threadIdx.x < nseg) s_src[threadIdx.x] = (const T *)src_ptrs[threadIdx.x];
     __syncthreads();
     for (int32_t e = blockIdx.x * kBlock + threadIdx.x; e < total; e += gridDim.x * kBlock) {
         int s = 0;
         while (e >= s_off[s + 1]) ++s;
-        const volatile double *src = s_src[s];   // peers write it: never cache in L1
-        x[dst_idx[e]] = src[src_idx != nullptr ? src_idx[e] : e - s_off[s]];
+        const volatile T *src = s_src[s];   // peers write it: never cache in L1
+        x[dst_idx[e]] = (double)src[src_idx != nullptr ? src_idx[e] : e - s_off[s]];
     }
 }
 
 void launch_halo_pull(const Ctx &ctx, int32_t nseg, const int32_t *seg_off_dev, int32_t total,
                       const int32_t *dst_idx, const int32_t *src_idx,
-                      const double *const *src_ptrs, double *x)
+                      const void *const *src_ptrs, double *x, bool f32)
 {
     if (nseg <= 0 || total <= 0) return;
     SCHWZ_REQUIRE(nseg <= kMaxSeg, "too many in-neighbours for one pull launch");
     ctx.use();
     int grid = std::max(1, std::min((total + kBlock - 1) / kBlock, kVecGrid));
-    halo_pull_kernel<<<grid, kBlock, 0, ctx.stream>>>(nseg, seg_off_dev, total, dst_idx, src_idx,
-                                                      src_ptrs, x);
+    if (f32)
+        halo_pull_kernel<float><<<grid, kBlock, 0, ctx.stream>>>(nseg, seg_off_dev, total, dst_idx,
+                                                                 src_idx, src_ptrs, x);
+    else
+        halo_pull_kernel<double><<<grid, kBlock, 0, ctx.stream>>>(nseg, seg_off_dev, total, dst_idx,
+                                                                  src_idx, src_ptrs, x);
     SCHWZ_CUDA(cudaGetLastError());
     count_launch();
 }

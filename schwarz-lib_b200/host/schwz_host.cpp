@@ -5,6 +5,7 @@
 // Reference being mirrored: source/schwarz_base.cpp (ctor :74-124, initialize
 // :128-271, run :323-506), source/restricted_schwarz.cpp, source/
 // initialization.cpp, source/solve.cpp, source/communicate.cpp.
+#include <type_traits>
 #include <algorithm>
 #include <cfloat>
 #include <cmath>
@@ -813,6 +814,10 @@ void SolverRAS<V, I, M>::setup_comm_buffers()
             o.non_symmetric = settings.non_symmetric_matrix ? 1 : 0;
             o.restart_iter = (int32_t)settings.restart_iter;
             o.overlap = settings.overlap;
+            // float mirrors of the halo buffers exist only when MixedValueType is float
+            // (restricted_schwarz.cpp:483-492); with M = double the conversion is the identity
+            o.use_mixed_precision =
+                (settings.use_mixed_precision && std::is_same<M, float>::value) ? 1 : 0;
             B200_CHECK(schwz_b200_ras_create(D.ctx, D.setup, me, this->rhs_host_.data(), &o, &D.ras));
             if (D.have_factors)
                 B200_CHECK(schwz_b200_ras_set_factors(D.ras, D.L_rowptr.data(), D.L_col.data(),

@@ -25,7 +25,7 @@ class RasOptions(C.Structure):
     _fields_ = [("tolerance", C.c_double), ("local_tol", C.c_double),
                 ("local_max_iters", C.c_int32), ("local_solver", C.c_int32),
                 ("non_symmetric", C.c_int32), ("restart_iter", C.c_int32),
-                ("overlap", C.c_int32), ("reserved", C.c_int32)]
+                ("overlap", C.c_int32), ("use_mixed_precision", C.c_int32)]
 
 
 class MailboxLayout(C.Structure):
@@ -520,12 +520,12 @@ class Ras:
 
     def __init__(self, ctx, setup, rank, rhs=None, tolerance=1e-6, local_tol=1e-12,
                  local_max_iters=-1, local_solver="iterative-ginkgo", non_symmetric=False,
-                 restart_iter=1):
+                 restart_iter=1, use_mixed_precision=False):
         self.ctx = ctx
         self.rank = rank
         o = RasOptions(tolerance, local_tol, local_max_iters,
                        {"iterative-ginkgo": 2, "direct-ginkgo": 1}[local_solver],
-                       int(non_symmetric), restart_iter, setup.overlap, 0)
+                       int(non_symmetric), restart_iter, setup.overlap, int(use_mixed_precision))
         h = C.c_void_p()
         rhs_arr = None if rhs is None else _f64(rhs)
         _chk(load().schwz_b200_ras_create(ctx.h, setup.h, C.c_int32(rank), _p(rhs_arr),

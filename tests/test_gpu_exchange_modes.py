@@ -122,3 +122,49 @@ def test_tree_protocol_step_by_step(sz):
         got = call([1, 1, 1, 1, 1])
     assert got == [P] * 5
     _close(ctxs, subs)
+
+
+@pytest.mark.parametrize("mode", ["put", "get"])
+def test_mixed_precision_wire_format_rounds_to_float(sz, mode):
+    """use_mixed_precision: gathered exchanges carry floats (half the NVLink bytes); the
+    receiver sees exactly (double)(float)value."""
+    P, n = 4, 24
+    setup = sz.Setup(("laplacian2d", n), P)
+    ctxs, subs = _build(sz, setup, P, use_mixed_precision=True)
+    f = lambda gid: np.sin(gid.astype(np.float64)) * 1e3 + gid / 7.0      # noqa: E731
+    fr = setup.first_row()
+    for r, s in enumerate(subs):
+        s.set_exchange_mode(mode)
+        s.set_x_own(f(np.arange(fr[r], fr[r + 1])))
+    for s in subs:
+        s.exchange_push(1)
+    for s in subs:
+        s.sync()
+    for s in subs:
+        s.exchange_unpack(1)
+    for r, s in enumerate(subs):
+        l2g = setup.l2g(r)
+        want = f(l2g)
+        want[s.local_size:] = want[s.local_size:].astype(np.float32).astype(np.float64)
+        assert np.array_equal(s.x(), want), (mode, r)
+    _close(ctxs, subs)
+
+
+def test_mixed_precision_sync_run_matches_oracle(sz, orc):
+    n, P = 24, 4
+    part = orc.partition_regular2d(n * n, P)
+    ob = orc.Problem(*orc.laplacian2d(n), P, part=part)
+    ob.configure(tolerance=1e-6, local_tol=1e-12, max_iters=400, enable_global_check=True,
+                 use_mixed_precision=True)
+    iters = ob.run()
+    setup = sz.Setup(("laplacian2d", n), P, part=part)
+    ctxs, subs = _build(sz, setup, P, local_tol=1e-12, use_mixed_precision=True)
+    out = sz.ras_run(subs, P, 400, tolerance=1e-6, enable_global_check=True, history=True)
+    assert out["converged"] and out["iters"] == iters
+    _, gres = ob.history(0)
+    np.testing.assert_allclose(out["history"].sum(axis=1), gres, rtol=1e-8, atol=1e-9)
+    for r in range(P):
+        l2g = setup.l2g(r)
+        xo = ob.x(r)[l2g]
+        assert np.linalg.norm(subs[r].x() - xo) <= 1e-9 * np.linalg.norm(xo)
+    _close(ctxs, subs)

@@ -264,3 +264,37 @@ def test_sptrsv_matches_oracle(gpu, sz, orc):
         for p in (db, dy, dz):
             gpu.free(p)
         tl.close(); tu.close()
+
+
+def test_fused_reductions_beyond_65536_row_tiles(gpu, sz, orc):
+    """cfg4's slabs have 17.3 M rows = 67.6 k row tiles: the persistent SpMV keeps one partial
+    per resident CTA, so the fused dot / norm must work past the 65 536-entry scratch (this
+    used to be rejected).  3-D 7-pt Laplacian 262^3 (18.0 M rows), CG against the row-sum
+    identity: A * 1 is the count of missing neighbours, checked bit-exactly against the
+    oracle's SpMV and through 3 CG iterations (fused p.q and ||r||) against the oracle's CG."""
+    n = 262
+    rp, ci, v = sz.laplacian3d(n)
+    N = n ** 3
+    assert N // 256 > 65536
+    A = sz.Csr(gpu, rp, ci, v)
+    ones = np.ones(N)
+    dx = gpu.to_device(ones)
+    dy = gpu.zeros(N)
+    A.spmv(dx, dy, 1.0, 0.0)
+    got = gpu.to_host(dy, N)
+    orc.set_threads(orc.max_threads())
+    assert np.array_equal(got, orc.spmv(rp, ci, v, ones))
+    cg = sz.Cg(gpu, A)
+    b = gpu.to_device(got)
+    x = gpu.zeros(N)
+    cg.solve(b, x, 3, 1e-30)
+    it, res, res0 = cg.result()
+    xo, ito = orc.cg(rp, ci, v, got, np.zeros(N), 3, 1e-30)
+    assert it == ito == 3
+    xg = gpu.to_host(x, N)
+    assert np.linalg.norm(xg - xo) <= 1e-12 * np.linalg.norm(xo)
+    assert res0 == pytest.approx(np.linalg.norm(got), rel=1e-13)
+    for p in (dx, dy, b, x):
+        gpu.free(p)
+    cg.close()
+    A.close()

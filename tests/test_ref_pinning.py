@@ -251,3 +251,37 @@ def test_onesided_put_one_by_one_is_broken_upstream(ref, orc):
     ob.run()
     assert rr.iter_count(0) == 400 and rr.iter_count(1) == 400
     assert ob.iter_count() < 400
+
+
+@pytest.mark.parametrize("onesided", [False, True])
+def test_mixed_precision_halo(ref, orc, onesided):
+    """settings.use_mixed_precision with MixedValueType = float (what the deal.II drivers of the
+    reference instantiate; bench_ras never sets it): halo values are rounded to float on the
+    wire (restricted_schwarz.cpp:483-603, 769-787, 898-903).  The reference is run as
+    SolverRAS<double, int32, float>."""
+    orc.set_threads(1)
+    n, P = 16, 4
+    kw = dict(max_iters=300, tolerance=1e-6, local_tol=1e-12)
+    part = orc.partition_regular2d(n * n, P)
+    if not onesided:
+        rr = ref.Run(P, laplacian_n=n, partition="regular2d", overlap=2, enable_global_check=True,
+                     record_iterates=True, use_mixed_precision=True, **kw)
+        ob = orc.Problem(*orc.laplacian2d(n), P, part=part)
+        ob.configure(enable_global_check=True, use_mixed_precision=True, **kw)
+        same_setup(rr, ob, P, True)
+        same_history(rr, ob, P)
+        # and it is a different run from the fp64 one
+        ob64 = orc.Problem(*orc.laplacian2d(n), P, part=part)
+        ob64.configure(enable_global_check=True, **kw)
+        ob64.run()
+        assert not np.array_equal(ob64.history(0)[0][:10], ob.history(0)[0][:10])
+    else:
+        rr = ref.Run(P, laplacian_n=n, partition="regular2d", overlap=2, enable_onesided=True,
+                     remote_comm_type="put", global_convergence_type="decentralized",
+                     use_mixed_precision=True, **kw)
+        ob = orc.Problem(*orc.laplacian2d(n), P, part=part)
+        ob.configure(enable_onesided=True, remote_comm_type="put",
+                     global_convergence_type="decentralized", use_mixed_precision=True, **kw)
+        same_setup(rr, ob, P, True)
+        ob.run()
+        assert all(rr.iter_count(r) < 300 for r in range(P)) and ob.iter_count() < 300
