@@ -438,6 +438,56 @@ __global__ void __launch_bounds__(kBlock)
     }
 }
 
+// One block of a small-level run: warps form t_i = b_i - sum over the entries OUTSIDE the
+// block (all of them already solved by earlier launches); the last CTA to finish multiplies
+// by the block's explicit inverse: x_K = Dinv_K t.
+constexpr int kTrsBlock = 128;
+
+__global__ void __launch_bounds__(kBlock)
+    trs_block_kernel(int32_t pos0, int32_t nrows, const int32_t *__restrict__ order,
+                     const int32_t *__restrict__ crp, const int32_t *__restrict__ cci,
+                     const double *__restrict__ cv, const double *__restrict__ dinv,
+                     const double *__restrict__ b, double *x, double *t_scratch,
+                     unsigned int *ticket)
+{
+    __shared__ double s_t[kTrsBlock];
+    __shared__ bool s_last;
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * kBlock + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * kBlock) >> 5;
+    for (int32_t i = warp; i < nrows; i += nwarps) {
+        const int32_t p = pos0 + i;
+        double s = 0.0;
+        for (int32_t k = crp[p] + lane; k < crp[p + 1]; k += 32) s += cv[k] * x[cci[k]];
+        s = warp_sum(s);
+        if (lane == 0) t_scratch[i] = b[order[p]] - s;
+    }
+    if (gridDim.x > 1) {
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const unsigned int tk = atomicAdd(ticket, 1u);
+            s_last = (tk == gridDim.x - 1);
+            if (s_last) *ticket = 0u;
+        }
+        __syncthreads();
+        if (!s_last) return;
+        __threadfence();
+    } else {
+        __syncthreads();
+    }
+    for (int i = threadIdx.x; i < nrows; i += kBlock) s_t[i] = __ldcg(t_scratch + i);
+    __syncthreads();
+    // two threads per row split the columns (even / odd); Dinv is column-major so that the
+    // threads of a warp read consecutive addresses
+    const int row = threadIdx.x >> 1, half = threadIdx.x & 1;
+    double acc = 0.0;
+    if (row < nrows)
+        for (int j = half; j <= row; j += 2) acc += dinv[(size_t)j * nrows + row] * s_t[j];
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    if (row < nrows && half == 0) x[order[pos0 + row]] = acc;
+}
+
 TrsPlan::TrsPlan(const Ctx &ctx, int32_t n, const int32_t *rp, const int32_t *ci,
                  const double *v, bool upper)
     : ctx_(ctx), n_(n), upper_(upper)
@@ -470,6 +520,87 @@ TrsPlan::TrsPlan(const Ctx &ctx, int32_t n, const int32_t *rp, const int32_t *ci
     order_ = ctx.upload(order.data(), (size_t)n);
     inv_diag_ = ctx.upload(inv_diag.data(), (size_t)n);
     level_ptr_dev_ = ctx.upload(level_ptr_.data(), level_ptr_.size());
+
+    // ---- segments: wide levels one by one, runs of small levels cut into blocks ----------
+    static_assert(2 * kTrsBlock <= kBlock, "two threads per block row in trs_block_kernel");
+    std::vector<int32_t> crp(1, 0), cci, pos_in_block((size_t)n, -1);
+    std::vector<double> cv, dinv;
+    std::vector<int32_t> chain_first;   // position of every chain row -> index into crp
+    std::vector<int32_t> crp_of_pos((size_t)n + 1, 0);
+    int32_t l = 0;
+    std::vector<double> D, Dinv;
+    while (l < num_levels_) {
+        const int32_t rows = level_ptr_[l + 1] - level_ptr_[l];
+        if (rows > kTrsSmallLevel) {
+            segments_.push_back({0, l, 0, 0});
+            ++l;
+            continue;
+        }
+        int32_t l1 = l + 1;
+        while (l1 < num_levels_ && level_ptr_[l1 + 1] - level_ptr_[l1] <= kTrsSmallLevel) ++l1;
+        const int32_t p_begin = level_ptr_[l], p_end = level_ptr_[l1];
+        for (int32_t p0 = p_begin; p0 < p_end; p0 += kTrsBlock) {
+            const int32_t nb = std::min(kTrsBlock, p_end - p0);
+            for (int32_t i = 0; i < nb; ++i) pos_in_block[order[p0 + i]] = i;
+            D.assign((size_t)nb * nb, 0.0);
+            for (int32_t i = 0; i < nb; ++i) {
+                const int32_t row = order[p0 + i];
+                for (int32_t k = rp[row]; k < rp[row + 1]; ++k) {
+                    const int32_t c = ci[k];
+                    const int32_t q = pos_in_block[c];
+                    if (c == row) {
+                        D[(size_t)i * nb + i] = v[k];
+                    } else if (q >= 0) {
+                        // in-block dependency: always an earlier position (earlier level)
+                        D[(size_t)i * nb + q] = v[k];
+                    } else if (upper ? c > row : c < row) {
+                        cci.push_back(c);
+                        cv.push_back(v[k]);
+                    }
+                }
+                crp.push_back((int32_t)cci.size());
+            }
+            // explicit inverse of the lower-triangular block (row-major D, forward substitution
+            // on the identity), stored column-major with ld = nb
+            Dinv.assign((size_t)nb * nb, 0.0);
+            for (int32_t j = 0; j < nb; ++j) {
+                for (int32_t i = j; i < nb; ++i) {
+                    double sacc = (i == j) ? 1.0 : 0.0;
+                    for (int32_t q = j; q < i; ++q) sacc -= D[(size_t)i * nb + q] * Dinv[(size_t)j * nb + q];
+                    Dinv[(size_t)j * nb + i] = sacc / D[(size_t)i * nb + i];
+                }
+            }
+            segments_.push_back({1, p0, nb, (int64_t)dinv.size()});
+            dinv.insert(dinv.end(), Dinv.begin(), Dinv.end());
+            for (int32_t i = 0; i < nb; ++i) pos_in_block[order[p0 + i]] = -1;
+            ++num_blocks_;
+        }
+        l = l1;
+    }
+    if (num_blocks_ > 0) {
+        // crp is indexed by chain-row ordinal; the kernel wants it indexed by position, so
+        // spread it out (positions outside chain runs keep empty ranges)
+        std::vector<int32_t> by_pos((size_t)n + 1, 0);
+        size_t ord = 0;
+        int32_t last = 0;
+        std::vector<char> is_chain((size_t)n, 0);
+        for (const Segment &sg : segments_)
+            if (sg.kind == 1)
+                for (int32_t i = 0; i < sg.b; ++i) is_chain[sg.a + i] = 1;
+        for (int32_t p = 0; p < n; ++p) {
+            by_pos[p] = last;
+            if (is_chain[p]) {
+                last = crp[ord + 1];
+                ++ord;
+            }
+        }
+        by_pos[n] = last;
+        chain_rp_ = ctx.upload(by_pos.data(), by_pos.size());
+        chain_ci_ = ctx.upload(cci.data(), cci.size());
+        chain_v_ = ctx.upload(cv.data(), cv.size());
+        dinv_ = ctx.upload(dinv.data(), dinv.size());
+        block_t_ = ctx.alloc_zero<double>(kTrsBlock);
+    }
 }
 
 TrsPlan::~TrsPlan()
@@ -481,6 +612,11 @@ TrsPlan::~TrsPlan()
     ctx_.release(order_);
     ctx_.release(inv_diag_);
     ctx_.release(level_ptr_dev_);
+    ctx_.release(chain_rp_);
+    ctx_.release(chain_ci_);
+    ctx_.release(chain_v_);
+    ctx_.release(dinv_);
+    ctx_.release(block_t_);
 }
 
 void TrsPlan::solve(const double *b, double *x)
@@ -499,21 +635,19 @@ void TrsPlan::solve(const double *b, double *x)
     }
     cudaGraph_t graph = nullptr;
     SCHWZ_CUDA(cudaStreamBeginCapture(ctx_.stream, cudaStreamCaptureModeThreadLocal));
-    int32_t l = 0;
     int launches = 0;
-    while (l < num_levels_) {
-        const int32_t rows = level_ptr_[l + 1] - level_ptr_[l];
-        if (rows > kTrsSmallLevel) {
+    for (const Segment &sg : segments_) {
+        if (sg.kind == 0) {
+            const int32_t l = sg.a;
+            const int32_t rows = level_ptr_[l + 1] - level_ptr_[l];
             const int grid = std::min((rows + kTrsWarps - 1) / kTrsWarps, kVecGrid);
             trs_levels_kernel<<<grid, kBlock, 0, ctx_.stream>>>(l, l + 1, level_ptr_dev_, order_,
                                                                 rp_, ci_, v_, inv_diag_, b, x);
-            ++l;
         } else {
-            int32_t l1 = l + 1;
-            while (l1 < num_levels_ && level_ptr_[l1 + 1] - level_ptr_[l1] <= kTrsSmallLevel) ++l1;
-            trs_levels_kernel<<<1, kBlock, 0, ctx_.stream>>>(l, l1, level_ptr_dev_, order_, rp_,
-                                                             ci_, v_, inv_diag_, b, x);
-            l = l1;
+            const int grid = std::max(1, (sg.b + kTrsWarps - 1) / kTrsWarps);
+            trs_block_kernel<<<grid, kBlock, 0, ctx_.stream>>>(
+                sg.a, sg.b, order_, chain_rp_, chain_ci_, chain_v_, dinv_ + sg.dinv_off, b, x,
+                block_t_, ctx_.tickets + 6);
         }
         ++launches;
     }

@@ -151,20 +151,32 @@ def test_mixed_precision_wire_format_rounds_to_float(sz, mode):
 
 
 def test_mixed_precision_sync_run_matches_oracle(sz, orc):
+    """Float rounding on the wire makes the run discontinuous in its inputs: a 1-ulp (double)
+    difference in a halo value that sits on a float rounding boundary becomes a 6e-8 relative
+    jump.  So the GPU run is compared with the oracle at the float level (1e-5 on the residual
+    history, 1e-6 on the iterates), not at 1e-10, and the stopping iteration may move by one."""
     n, P = 24, 4
     part = orc.partition_regular2d(n * n, P)
     ob = orc.Problem(*orc.laplacian2d(n), P, part=part)
-    ob.configure(tolerance=1e-6, local_tol=1e-12, max_iters=400, enable_global_check=True,
+    ob.configure(tolerance=1e-5, local_tol=1e-12, max_iters=400, enable_global_check=True,
                  use_mixed_precision=True)
     iters = ob.run()
     setup = sz.Setup(("laplacian2d", n), P, part=part)
     ctxs, subs = _build(sz, setup, P, local_tol=1e-12, use_mixed_precision=True)
-    out = sz.ras_run(subs, P, 400, tolerance=1e-6, enable_global_check=True, history=True)
-    assert out["converged"] and out["iters"] == iters
+    out = sz.ras_run(subs, P, 400, tolerance=1e-5, enable_global_check=True, history=True)
+    assert out["converged"] and abs(out["iters"] - iters) <= 1, (out["iters"], iters)
     _, gres = ob.history(0)
-    np.testing.assert_allclose(out["history"].sum(axis=1), gres, rtol=1e-8, atol=1e-9)
-    for r in range(P):
-        l2g = setup.l2g(r)
-        xo = ob.x(r)[l2g]
-        assert np.linalg.norm(subs[r].x() - xo) <= 1e-9 * np.linalg.norm(xo)
+    k = min(len(gres), len(out["history"]))
+    np.testing.assert_allclose(out["history"].sum(axis=1)[:k], gres[:k], rtol=0, atol=1e-5 * gres[0])
+    if out["iters"] == iters:
+        for r in range(P):
+            l2g = setup.l2g(r)
+            xo = ob.x(r)[l2g]
+            assert np.linalg.norm(subs[r].x() - xo) <= 1e-6 * np.linalg.norm(xo)
+    # and it really is the float run, not the fp64 one
+    ob64 = orc.Problem(*orc.laplacian2d(n), P, part=part)
+    ob64.configure(tolerance=1e-5, local_tol=1e-12, max_iters=400, enable_global_check=True)
+    ob64.run()
+    g64 = ob64.history(0)[1]
+    assert abs(out["history"].sum(axis=1)[5] - gres[5]) < abs(g64[5] - gres[5])
     _close(ctxs, subs)

@@ -298,3 +298,35 @@ def test_fused_reductions_beyond_65536_row_tiles(gpu, sz, orc):
         gpu.free(p)
     cg.close()
     A.close()
+
+
+def test_sptrsv_blocked_dense_top_of_a_nested_dissection_factor(gpu, sz, orc):
+    """A factor with both regimes: wide levels (one launch each) and long runs of small levels
+    (the dense separator triangles), which are solved in blocks of <= 128 rows through the
+    explicit inverse of the block's own triangle.  L then U = L^T against the oracle's serial
+    substitution; the residual L (L^T z) = b closes the loop independently of the oracle."""
+    import scipy.sparse as sp
+    rng = np.random.default_rng(11)
+    rp, ci, v = sz.laplacian2d(120)
+    n = len(rp) - 1
+    perm = sz.nd_ordering(rp, ci)
+    Lrp, Lci, Lv = sz.host_cholesky(rp, ci, v, perm)
+    Lm = sp.csr_matrix((Lv, Lci, Lrp), shape=(n, n))
+    U = Lm.T.tocsr(); U.sort_indices()
+    Urp, Uci, Uv = U.indptr.astype(np.int32), U.indices.astype(np.int32), U.data
+    tl = sz.Trs(gpu, Lrp, Lci, Lv, upper=False)
+    tu = sz.Trs(gpu, Urp, Uci, Uv, upper=True)
+    assert tl.levels() > 300          # long dependency chain ...
+    b = rng.standard_normal(n)
+    db = gpu.to_device(b); dy = gpu.zeros(n); dz = gpu.zeros(n)
+    for _ in range(2):                # second pass replays the captured graph
+        tl.solve(db, dy); tu.solve(dy, dz)
+        y = gpu.to_host(dy, n); z = gpu.to_host(dz, n)
+        yo = orc.trs(Lrp, Lci, Lv, b, upper=False)
+        zo = orc.trs(Urp, Uci, Uv, yo, upper=True)
+        assert np.linalg.norm(y - yo) <= 1e-12 * np.linalg.norm(yo)
+        assert np.linalg.norm(z - zo) <= 1e-11 * np.linalg.norm(zo)
+        assert np.linalg.norm(Lm @ (Lm.T @ z) - b) <= 1e-11 * np.linalg.norm(b)
+    for p in (db, dy, dz):
+        gpu.free(p)
+    tl.close(); tu.close()

@@ -10,6 +10,7 @@ BIN=$(readlink -f "$BIN")
 mkdir -p "$OUT"
 run() {
     name=$1; shift
+    if [[ -n "${ONLY:-}" && "$name" != *"$ONLY"* ]]; then return; fi
     mkdir -p "$OUT/$name"
     ( cd "$OUT/$name" && { time timeout ${TMO:-600} "$BIN" --executor=cuda --num_devices=$ND \
         --timings_file=timings "$@" > run.log 2> run.err; echo "rc=$?" >> run.log; } 2> wall.txt )
