@@ -42,12 +42,27 @@ def parse():
     ap.add_argument("--n", type=int, default=8192, help="1-D Laplacian size (grid is n x n)")
     ap.add_argument("--subdomains", type=int, default=8)
     ap.add_argument("--local-iters", type=int, default=50, help="--local_max_iters of bench_ras")
+    ap.add_argument("--dim", type=int, default=2, choices=[2, 3],
+                    help="2: 5-pt Laplacian n x n (cfg2); 3: 7-pt Laplacian n^3 (cfg4, use --n 512)")
+    ap.add_argument("--onesided", action="store_true",
+                    help="one-sided Put exchange + decentralised convergence flags (cfg4)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
 
 
 def workload(args):
+    if args.dim == 3:
+        return {
+            "workload": "cfg4: 3D 7-pt Laplacian %d^3 fp64/int32, %d subdomains (regular 1-D slabs, "
+                        "overlap 2), CG local solve local_max_iters=%d local_tol=1e-12, %s"
+                        % (args.n, args.subdomains, args.local_iters,
+                           "one-sided Put exchange, decentralised convergence flags" if args.onesided
+                           else "synchronous halo exchange, enable_global_check"),
+            "n": args.n, "dim": 3, "subdomains": args.subdomains,
+            "local_max_iters": args.local_iters, "overlap": 2, "partition": "regular",
+            "l2_policy": "inputs larger than L2 (each local CSR is ~1.7 GB vs 126 MB L2)",
+        }
     return {
         "workload": "cfg2: 2D 5-pt Laplacian %dx%d fp64/int32, %d subdomains (regular 1-D strips, "
                     "overlap 2), CG local solve local_max_iters=%d local_tol=1e-12, synchronous "
@@ -135,9 +150,9 @@ def cpu_sample(args, steps=1):
     import schwz_b200 as S
     cores = O.max_threads()
     O.set_threads(cores)
-    key = (args.n, args.subdomains)
+    key = (args.dim, args.n, args.subdomains)
     if key not in _CPU_CACHE:
-        setup = S.Setup(("laplacian2d", args.n), args.subdomains)
+        setup = S.Setup(("laplacian3d" if args.dim == 3 else "laplacian2d", args.n), args.subdomains)
         r = min(1, args.subdomains - 1)          # an interior strip when there is one
         _CPU_CACHE[key] = setup.local_matrix(r)
         del setup
@@ -214,7 +229,7 @@ def main():
     torch.cuda.set_device(dev)
 
     # ---- setup (host index sets, upload) — outside every timed region --------
-    setup = S.Setup(("laplacian2d", args.n), P)
+    setup = S.Setup(("laplacian3d" if args.dim == 3 else "laplacian2d", args.n), P)
     ctxs = [S.Context(dev) for _ in my]
     subs = []
     for c, r in zip(ctxs, my):
@@ -256,6 +271,9 @@ def main():
             torch.cuda.synchronize()
 
     def run_steps(k):
+        if args.onesided:
+            return S.ras_run(subs, P, k, tolerance=1e-6, enable_onesided=True,
+                             conv_decentralized=True, comm=comm)
         return S.ras_run(subs, P, k, tolerance=1e-6, enable_global_check=True, comm=comm)
 
     # ---- warm-up, then exactly K timed steps ---------------------------------
@@ -312,12 +330,29 @@ def main():
             "launch_ms": k0["ms"], "share_of_step": per_step_spmv_ms / (ms / args.steps),
             "other_kernels": {k: v for k, v in kern.items() if k != "csr_spmv_tma_kernel<EPI_DOT>"}}
 
+    # ---- halo exchange: push (pack + peer stores) + unpack of the subdomain of this rank that
+    # has a neighbour on another GPU when there is one (NVLink), else a same-GPU neighbour ----
+    # (every subdomain of every rank runs the same number of exchanges so that the epoch
+    # counters of neighbours stay in step for the e2e run below)
+    sb = subs[-1] if (world > 1 and rank < world - 1) else subs[0]
+    barrier()
+    halo_all = {s.rank: s.kernel_time_ms(4, 20) for s in subs}
+    barrier()
+    halo_ms = halo_all[sb.rank]
+    halo_bytes = sb.kernel_bytes(4)
+    halo = {"subdomain": sb.rank, "push_unpack_ms": halo_ms, "algorithmic_bytes": halo_bytes,
+            "GB/s": halo_bytes / (halo_ms * 1e-3) / 1e9,
+            "payload_bytes_out": 8 * sum(len(setup.put_list(sb.rank, j))
+                                         for j in range(len(setup.neighbors(sb.rank)[1]))),
+            "link": "nvlink peer stores to the next GPU + local" if world > 1 and rank < world - 1
+                    else "same GPU"}
+
     # ---- e2e: the plugin call with HOST buffers ------------------------------
     # rhs (pinned host) -> device, zero initial state, K outer iterations (each
     # reads the residual norms back, as the reference does), solution -> host.
     e2e = None
     if not args.no_e2e:
-        N = args.n * args.n
+        N = args.n ** args.dim
         rhs = torch.ones(N, dtype=torch.float64).pin_memory()
         sol = torch.zeros(N, dtype=torch.float64).pin_memory()
         barrier()
@@ -362,7 +397,7 @@ def main():
                "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                "dtype": "f64", "data": "synthetic", "config": workload(args),
                "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof,
-               "cpu_baseline": cpu, "wall_ms_per_step": 1e3 * wall / args.steps,
+               "cpu_baseline": cpu, "halo": halo, "wall_ms_per_step": 1e3 * wall / args.steps,
                "global_resnorm": res["global_resnorm"], "impl": "b200"}
         print(json.dumps(out))
 

@@ -837,6 +837,12 @@ int64_t schwz_b200_ras_kernel_bytes(schwz_ras *r, int32_t kind)
     case 1: return 48 * n;                                            // x,r,p,q read; x,r write
     case 2: return 24 * n;                                            // r,p read; p write
     case 3: return 12 * nnz + 4 * (n + 1) + 8 * n + 8 * n + 8 * n;    // + rhs read
+    case 4: {                                                         // push + unpack: 20 B/element
+        int64_t e = 0;
+        for (int32_t c : R.in_count) e += c;
+        for (int32_t c : R.out_count) e += c;
+        return 20 * e;
+    }
     default: return 0;
     }
 }
