@@ -39,7 +39,8 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--n", type=int, default=8192, help="1-D Laplacian size (grid is n x n)")
+    ap.add_argument("--n", "--size", dest="n", type=int, default=8192,
+                    help="1-D Laplacian size (grid is n x n, or n^3 with --dim 3); use --size under torchrun")
     ap.add_argument("--subdomains", type=int, default=8)
     ap.add_argument("--local-iters", type=int, default=50, help="--local_max_iters of bench_ras")
     ap.add_argument("--dim", type=int, default=2, choices=[2, 3],
