@@ -318,6 +318,7 @@ float Ras::kernel_time_ms(int kind, int reps)
         default: SCHWZ_REQUIRE(cg != nullptr, "no CG solver on this subdomain"); cg->bench_step(kind, work);
         }
     };
+    if ((kind == 1 || kind == 2) && cg) cg->bench_step(-1, work);
     one();
     SCHWZ_CUDA(cudaEventRecord(ctx.ev_start, ctx.stream));
     for (int i = 0; i < reps; ++i) one();

@@ -13,6 +13,13 @@ reps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
 setup = S.Setup(("laplacian2d", n), 8)
 ctx = S.Context(0)
 sub = S.Ras(ctx, setup, 1, local_max_iters=50)
+# one real local solve first, so that the CG scalars (rho, beta, iteration count) hold live
+# values: with the zero-initialised ones the vector kernels take their degenerate branches
+# (beta == 0 skips the x/r update, iteration 0 turns the p update into a copy)
+sub.update_boundary()
+sub.local_residual()
+sub.local_solve()
+sub.sync()
 for kind, name in ((0, "spmv+dot"), (3, "residual spmv+norm"), (1, "cg x/r update"), (2, "cg p update")):
     ms = sub.kernel_time_ms(kind, reps)
     b = sub.kernel_bytes(kind)
