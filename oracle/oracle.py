@@ -45,7 +45,12 @@ class OrcOptions(C.Structure):
         ("enable_accumulate", C.c_int32),
         ("iter_offset", C.c_int32),
         ("use_mixed_precision", C.c_int32),
+        ("local_precond", C.c_int32),
+        ("precond_max_block_size", C.c_int32),
     ]
+
+
+PRECOND = {"null": 0, "block-jacobi": 1, "ilu": 2, "isai": 3}
 
 
 _lib = None
@@ -121,22 +126,73 @@ def spmv(rp, ci, v, x, alpha=1.0, beta=0.0, y=None):
     return out
 
 
-def cg(rp, ci, v, b, x0, max_iters, factor):
+class Precond:
+    """Local preconditioner of the iterative local solve (source/solve.cpp:486-652):
+    kind in PRECOND.  Restated Ginkgo semantics, pinned to oracle/_ref's stand-in."""
+
+    def __init__(self, rp, ci, v, kind, max_block_size=16):
+        L = lib()
+        L.orc_precond_create.restype = C.c_void_p
+        for f in ("orc_precond_block_ptrs", "orc_precond_blocks", "orc_precond_csr"):
+            getattr(L, f).restype = C.c_int64
+        self.n = len(rp) - 1
+        self.kind = kind
+        self.h = C.c_void_p(L.orc_precond_create(
+            C.c_int32(self.n), _p(np.ascontiguousarray(rp, np.int32)),
+            _p(np.ascontiguousarray(ci, np.int32)), _p(np.ascontiguousarray(v, np.float64)),
+            C.c_int(PRECOND[kind]), C.c_int(max_block_size)))
+
+    def __del__(self):
+        try:
+            if self.h:
+                lib().orc_precond_free(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def apply(self, r):
+        r = np.ascontiguousarray(r, np.float64)
+        z = np.zeros(self.n)
+        lib().orc_precond_apply(self.h, C.c_int32(self.n), _p(r), _p(z))
+        return z
+
+    def block_ptrs(self):
+        out = np.zeros(lib().orc_precond_block_ptrs(self.h, None), np.int32)
+        lib().orc_precond_block_ptrs(self.h, _p(out))
+        return out
+
+    def blocks(self):
+        out = np.zeros(lib().orc_precond_blocks(self.h, None), np.float64)
+        lib().orc_precond_blocks(self.h, _p(out))
+        return out
+
+    def csr(self, which):
+        """0 L, 1 U of the ILU; 2 / 3 approximate inverses of L / U (ISAI)."""
+        nnz = lib().orc_precond_csr(self.h, C.c_int(which), None, None, None)
+        rp = np.zeros(self.n + 1, np.int32)
+        ci = np.zeros(nnz, np.int32)
+        v = np.zeros(nnz, np.float64)
+        lib().orc_precond_csr(self.h, C.c_int(which), _p(rp), _p(ci), _p(v))
+        return rp, ci, v
+
+
+def cg(rp, ci, v, b, x0, max_iters, factor, precond=None):
     n = len(rp) - 1
     x = np.array(x0, dtype=np.float64)
-    it = lib().orc_cg(C.c_int32(n), _p(rp), _p(ci), _p(v),
-                      _p(np.ascontiguousarray(b, np.float64)), _p(x),
-                      C.c_int(max_iters), C.c_double(factor))
+    it = lib().orc_cg_pc(C.c_int32(n), _p(rp), _p(ci), _p(v),
+                         _p(np.ascontiguousarray(b, np.float64)), _p(x),
+                         C.c_int(max_iters), C.c_double(factor),
+                         precond.h if precond is not None else None)
     return x, int(it)
 
 
-def gmres(rp, ci, v, b, x0, max_iters, factor, restart):
+def gmres(rp, ci, v, b, x0, max_iters, factor, restart, precond=None):
     n = len(rp) - 1
     x = np.array(x0, dtype=np.float64)
-    it = lib().orc_gmres(C.c_int32(n), _p(rp), _p(ci), _p(v),
-                         _p(np.ascontiguousarray(b, np.float64)), _p(x),
-                         C.c_int(max_iters), C.c_double(factor),
-                         C.c_int(restart))
+    it = lib().orc_gmres_pc(C.c_int32(n), _p(rp), _p(ci), _p(v),
+                            _p(np.ascontiguousarray(b, np.float64)), _p(x),
+                            C.c_int(max_iters), C.c_double(factor),
+                            C.c_int(restart), precond.h if precond is not None else None)
     return x, int(it)
 
 
@@ -286,7 +342,8 @@ class Problem:
                   enable_global_check=False,
                   global_convergence_type="centralized-tree",
                   enable_accumulate=False, iter_offset=False, factor_perms=None,
-                  use_mixed_precision=False):
+                  use_mixed_precision=False, local_precond="null",
+                  precond_max_block_size=16):
         o = OrcOptions()
         o.tolerance = tolerance
         o.local_tol = local_tol
@@ -304,6 +361,8 @@ class Problem:
         o.enable_accumulate = int(enable_accumulate)
         o.iter_offset = int(iter_offset)
         o.use_mixed_precision = int(use_mixed_precision)
+        o.local_precond = PRECOND[local_precond]
+        o.precond_max_block_size = precond_max_block_size
         perm_all = None
         if factor_perms is not None:
             perm_all = np.ascontiguousarray(np.concatenate(factor_perms), np.int32)

@@ -201,3 +201,75 @@ class Run:
 
     def global_matrix(self, r=0):
         return self.vec("global_rp", r), self.vec("global_ci", r), self.vec("global_v", r)
+
+
+# ---- kernel-level probes of the Ginkgo stand-in (ref_shim/ref_driver.cpp) -------------------
+def _ip(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Precond:
+    """A preconditioner built with the builder calls of source/solve.cpp:486-652 on a CSR."""
+
+    def __init__(self, rp, ci, v, kind, max_block_size=16):
+        L = lib()
+        L.ref_precond_create.restype = C.c_void_p
+        L.ref_precond_csr.restype = C.c_int64
+        self.n = len(rp) - 1
+        self.rp = np.ascontiguousarray(rp, np.int32)
+        self.ci = np.ascontiguousarray(ci, np.int32)
+        self.v = np.ascontiguousarray(v, np.float64)
+        self.kind = kind
+        self.h = C.c_void_p(L.ref_precond_create(C.c_int(self.n), _ip(self.rp), _ip(self.ci),
+                                                 _ip(self.v), kind.encode(),
+                                                 C.c_int(max_block_size)))
+
+    def __del__(self):
+        try:
+            if self.h:
+                lib().ref_precond_free(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def apply(self, b):
+        b = np.ascontiguousarray(b, np.float64)
+        x = np.zeros(self.n)
+        lib().ref_precond_apply(self.h, _ip(b), _ip(x))
+        return x
+
+    def block_ptrs(self):
+        n = lib().ref_precond_block_ptrs(self.h, None, C.c_int64(0))
+        out = np.zeros(n, np.int32)
+        lib().ref_precond_block_ptrs(self.h, _ip(out), C.c_int64(n))
+        return out
+
+    def blocks(self):
+        n = lib().ref_precond_blocks(self.h, None, C.c_int64(0))
+        out = np.zeros(n, np.float64)
+        lib().ref_precond_blocks(self.h, _ip(out), C.c_int64(n))
+        return out
+
+    def csr(self, which):
+        """0 L, 1 U of the ILU; 2 / 3 approximate inverses of L / U (ISAI)."""
+        nnz = lib().ref_precond_csr(self.h, C.c_int(which), None, None, None)
+        if nnz < 0:
+            raise ValueError("this preconditioner has no matrix %d" % which)
+        rp = np.zeros(self.n + 1, np.int32)
+        ci = np.zeros(nnz, np.int32)
+        v = np.zeros(nnz, np.float64)
+        lib().ref_precond_csr(self.h, C.c_int(which), _ip(rp), _ip(ci), _ip(v))
+        return rp, ci, v
+
+
+def krylov_solve(rp, ci, v, b, x0, max_iters, tol, gmres=False, restart=1, precond=None):
+    """gko::solver::Cg / Gmres of the stand-in with the reference's stopping criteria."""
+    rp = np.ascontiguousarray(rp, np.int32)
+    ci = np.ascontiguousarray(ci, np.int32)
+    v = np.ascontiguousarray(v, np.float64)
+    b = np.ascontiguousarray(b, np.float64)
+    x = np.array(x0, np.float64, copy=True)
+    lib().ref_krylov_solve(C.c_int(len(rp) - 1), _ip(rp), _ip(ci), _ip(v), _ip(b), _ip(x),
+                           C.c_int(int(gmres)), C.c_int(restart), C.c_int(max_iters),
+                           C.c_double(tol), precond.h if precond is not None else None)
+    return x

@@ -9,8 +9,10 @@
 //   * solver::Cg / Gmres with Combined(Iteration, ResidualNormReduction) criteria,
 //     following the Ginkgo recurrences restated in SURVEY.md Appendix F;
 //   * solver::LowerTrs / UpperTrs (serial substitution);
-//   * preconditioner / factorization types exist so the reference compiles; only scalar
-//     Jacobi (max_block_size == 1) is implemented, the rest throw NotSupported.
+//   * preconditioner::Jacobi (block detection by supervariable agglomeration, Gauss-Jordan
+//     block inverses), factorization::ParIlu (one sequential sweep = ILU(0)),
+//     preconditioner::Ilu over LowerTrs/UpperTrs or LowerIsai/UpperIsai, restated from the
+//     upstream reference-executor kernels as remembered [upstream-memory].
 // What it proves: every integer/index set, buffer layout, exchange and convergence
 // protocol coming out of oracle/_ref is produced by the reference's own code. What it does
 // not prove: bit-level agreement with upstream Ginkgo's kernels (not in the tree).
@@ -1012,9 +1014,184 @@ public:
 
 }  // namespace stop
 
+// -------------------------------------------------------------------- factorization
+// ParILU on the reference executor [upstream-memory, Ginkgo 1.2/1.3 reference kernels]:
+// L takes the strictly lower part of A plus a unit diagonal, U the upper part incl. the
+// diagonal (a missing diagonal entry is added as a zero and initialised to one in U); then
+// `iterations` (default 0 -> 1) sequential sweeps of the Chow-Patel fixed-point update over
+// the entries of A in row-major order.  One sweep in that order reproduces ILU(0) exactly.
+namespace factorization {
+
+template <typename V = default_precision, typename I = int32>
+class ParIlu : public LinOp {   // stands for the Composition(L, U) upstream returns
+public:
+    class Factory;
+    struct parameters_type {
+        size_type iterations = 0;
+        bool skip_sorting = false;
+        parameters_type &with_iterations(size_type n)
+        {
+            iterations = n;
+            return *this;
+        }
+        parameters_type &with_skip_sorting(bool b)
+        {
+            skip_sorting = b;
+            return *this;
+        }
+        GKO_SHIM_ON(Factory)
+    };
+    class Factory : public LinOpFactory {
+    public:
+        Factory(std::shared_ptr<const Executor> e, const parameters_type &p)
+            : LinOpFactory(std::move(e)), params_(p)
+        {}
+        std::unique_ptr<ParIlu> generate(std::shared_ptr<const LinOp> op) const
+        {
+            return std::unique_ptr<ParIlu>(new ParIlu(exec_, params_, std::move(op)));
+        }
+
+    protected:
+        std::unique_ptr<LinOp> generate_impl(std::shared_ptr<const LinOp> op) const override
+        {
+            return generate(std::move(op));
+        }
+        parameters_type params_;
+    };
+    static parameters_type build() { return {}; }
+    std::shared_ptr<const matrix::Csr<V, I>> get_l_factor() const { return l_; }
+    std::shared_ptr<const matrix::Csr<V, I>> get_u_factor() const { return u_; }
+
+protected:
+    ParIlu(std::shared_ptr<const Executor> e, const parameters_type &p,
+           std::shared_ptr<const LinOp> op)
+        : LinOp(e, op->get_size())
+    {
+        auto A0 = as<matrix::Csr<V, I>>(op.get());
+        auto As = matrix::Csr<V, I>::create(e);
+        As->copy_from(A0);
+        if (!p.skip_sorting) As->sort_by_column_index();
+        const size_type n = As->get_size()[0];
+        // add_diagonal_elements: rows without a stored diagonal get an explicit zero
+        std::vector<I> rp(n + 1, 0), ci;
+        std::vector<V> va;
+        {
+            const I *arp = As->get_const_row_ptrs();
+            const I *aci = As->get_const_col_idxs();
+            const V *ava = As->get_const_values();
+            for (size_type r = 0; r < n; ++r) {
+                bool placed = false;
+                for (I k = arp[r]; k < arp[r + 1]; ++k) {
+                    if (!placed && static_cast<size_type>(aci[k]) > r) {
+                        ci.push_back(static_cast<I>(r));
+                        va.push_back(zero<V>());
+                        placed = true;
+                    }
+                    if (static_cast<size_type>(aci[k]) == r) placed = true;
+                    ci.push_back(aci[k]);
+                    va.push_back(ava[k]);
+                }
+                if (!placed) {
+                    ci.push_back(static_cast<I>(r));
+                    va.push_back(zero<V>());
+                }
+                rp[r + 1] = static_cast<I>(ci.size());
+            }
+        }
+        // initialize_row_ptrs_l_u + initialize_l_u
+        std::vector<I> lrp(n + 1, 0), urp(n + 1, 0);
+        for (size_type r = 0; r < n; ++r) {
+            I nl = 0, nu = 0;
+            for (I k = rp[r]; k < rp[r + 1]; ++k) {
+                if (static_cast<size_type>(ci[k]) < r) ++nl;
+                if (static_cast<size_type>(ci[k]) > r) ++nu;
+            }
+            lrp[r + 1] = lrp[r] + nl + 1;
+            urp[r + 1] = urp[r] + nu + 1;
+        }
+        auto L = matrix::Csr<V, I>::create(e, dim<2>(n, n), static_cast<size_type>(lrp[n]));
+        auto U = matrix::Csr<V, I>::create(e, dim<2>(n, n), static_cast<size_type>(urp[n]));
+        std::copy(lrp.begin(), lrp.end(), L->get_row_ptrs());
+        std::copy(urp.begin(), urp.end(), U->get_row_ptrs());
+        for (size_type r = 0; r < n; ++r) {
+            I il = lrp[r], iu = urp[r] + 1;   // U: the diagonal goes first
+            V diag = one<V>();
+            for (I k = rp[r]; k < rp[r + 1]; ++k) {
+                const size_type c = static_cast<size_type>(ci[k]);
+                if (c < r) {
+                    L->get_col_idxs()[il] = ci[k];
+                    L->get_values()[il] = va[k];
+                    ++il;
+                } else if (c == r) {
+                    diag = va[k];
+                } else {
+                    U->get_col_idxs()[iu] = ci[k];
+                    U->get_values()[iu] = va[k];
+                    ++iu;
+                }
+            }
+            L->get_col_idxs()[lrp[r + 1] - 1] = static_cast<I>(r);
+            L->get_values()[lrp[r + 1] - 1] = one<V>();
+            U->get_col_idxs()[urp[r]] = static_cast<I>(r);
+            U->get_values()[urp[r]] = diag != zero<V>() ? diag : one<V>();
+        }
+        // the sweep works on U stored by columns (CSR of U^T), exactly as upstream
+        auto Ut = std::unique_ptr<matrix::Csr<V, I>>(
+            static_cast<matrix::Csr<V, I> *>(U->transpose().release()));
+        const I *lr = L->get_const_row_ptrs(), *lc = L->get_const_col_idxs();
+        const I *ur = Ut->get_const_row_ptrs(), *uc = Ut->get_const_col_idxs();
+        V *lv = L->get_values(), *uv = Ut->get_values();
+        const size_type sweeps = p.iterations == 0 ? 1 : p.iterations;
+        for (size_type it = 0; it < sweeps; ++it)
+            for (size_type row = 0; row < n; ++row)
+                for (I el = rp[row]; el < rp[row + 1]; ++el) {
+                    const size_type col = static_cast<size_type>(ci[el]);
+                    I row_l = lr[row], row_u = ur[col];
+                    V sum = va[el], last_operation = zero<V>();
+                    while (row_l < lr[row + 1] && row_u < ur[col + 1]) {
+                        const I col_l = lc[row_l], col_u = uc[row_u];
+                        if (col_l == col_u) {
+                            last_operation = lv[row_l] * uv[row_u];
+                            sum -= last_operation;
+                        } else {
+                            last_operation = zero<V>();
+                        }
+                        if (col_l <= col_u) ++row_l;
+                        if (col_u <= col_l) ++row_u;
+                    }
+                    sum += last_operation;   // undo the term that contains the unknown itself
+                    if (row > col) {
+                        const V to_write = sum / uv[ur[col + 1] - 1];
+                        if (std::isfinite(to_write)) lv[row_l - 1] = to_write;
+                    } else {
+                        if (std::isfinite(sum)) uv[row_u - 1] = sum;
+                    }
+                }
+        l_ = std::move(L);
+        u_ = std::shared_ptr<matrix::Csr<V, I>>(
+            static_cast<matrix::Csr<V, I> *>(Ut->transpose().release()));
+    }
+    void apply_impl(const LinOp *, LinOp *) const override
+    {
+        throw NotSupported("ParIlu composition apply");
+    }
+    void apply_impl(const LinOp *, const LinOp *, const LinOp *, LinOp *) const override
+    {
+        throw NotSupported("ParIlu composition apply");
+    }
+    std::shared_ptr<matrix::Csr<V, I>> l_, u_;
+};
+
+}  // namespace factorization
+
 // -------------------------------------------------------------------- preconditioners
 namespace preconditioner {
 
+// Block-Jacobi [upstream-memory, Ginkgo reference kernels jacobi::find_blocks / generate /
+// simple_apply]: natural blocks = runs of consecutive rows with identical column pattern
+// (capped at max_block_size), agglomerated greedily while the sum stays <= max_block_size;
+// every diagonal block is inverted by in-place Gauss-Jordan with implicit row pivoting and
+// applied as a dense block times vector, inner index ascending.
 template <typename V = default_precision, typename I = int32>
 class Jacobi : public LinOp {
 public:
@@ -1046,81 +1223,298 @@ public:
         parameters_type params_;
     };
     static parameters_type build() { return {}; }
+    size_type get_num_blocks() const { return block_ptrs_.size() - 1; }
+    const std::vector<I> &get_block_pointers() const { return block_ptrs_; }
+    const std::vector<V> &get_blocks() const { return blocks_; }   // column-major, ld = block size
 
 protected:
     Jacobi(std::shared_ptr<const Executor> e, const parameters_type &p,
            std::shared_ptr<const LinOp> op)
         : LinOp(e, op->get_size())
     {
-        if (p.max_block_size != 1)
-            throw NotSupported("block-Jacobi with max_block_size > 1 (block detection of upstream "
-                               "Ginkgo is not restated; use --precond_max_block_size=1)");
+        if (p.max_block_size < 1 || p.max_block_size > 32)
+            throw NotSupported("Jacobi max_block_size outside [1, 32]");
         auto A = as<matrix::Csr<V, I>>(op.get());
-        inv_diag_.assign(A->get_size()[0], one<V>());
-        for (size_type r = 0; r < A->get_size()[0]; ++r)
-            for (I k = A->get_const_row_ptrs()[r]; k < A->get_const_row_ptrs()[r + 1]; ++k)
-                if (static_cast<size_type>(A->get_const_col_idxs()[k]) == r)
-                    inv_diag_[r] = one<V>() / A->get_const_values()[k];
+        const size_type n = A->get_size()[0];
+        const I *rp = A->get_const_row_ptrs();
+        const I *ci = A->get_const_col_idxs();
+        const V *va = A->get_const_values();
+        const I mbs = static_cast<I>(p.max_block_size);
+        // find_natural_blocks
+        std::vector<I> bp(n + 1, 0);
+        size_type nb = 0;
+        if (n > 0) {
+            nb = 1;
+            I cur = 1;
+            for (size_type i = 1; i < n; ++i) {
+                const I *prev = ci + rp[i - 1], *curr = ci + rp[i], *next = ci + rp[i + 1];
+                const bool same = (next - curr) == (curr - prev) && std::equal(curr, next, prev);
+                if (cur < mbs && same) {
+                    ++cur;
+                } else {
+                    bp[nb] = bp[nb - 1] + cur;
+                    ++nb;
+                    cur = 1;
+                }
+            }
+            bp[nb] = bp[nb - 1] + cur;
+        }
+        // agglomerate_supervariables
+        size_type na = 0;
+        if (nb > 0) {
+            na = 1;
+            I cur = bp[1] - bp[0];
+            for (size_type i = 1; i < nb; ++i) {
+                const I bs = bp[i + 1] - bp[i];
+                if (cur + bs <= mbs) {
+                    cur += bs;
+                } else {
+                    bp[na] = bp[na - 1] + cur;
+                    ++na;
+                    cur = bs;
+                }
+            }
+            bp[na] = bp[na - 1] + cur;
+        }
+        block_ptrs_.assign(bp.begin(), bp.begin() + na + 1);
+        block_off_.assign(na + 1, 0);
+        for (size_type b = 0; b < na; ++b) {
+            const size_type bs = static_cast<size_type>(block_ptrs_[b + 1] - block_ptrs_[b]);
+            block_off_[b + 1] = block_off_[b] + bs * bs;
+        }
+        blocks_.assign(block_off_[na], zero<V>());
+        std::vector<V> blk;
+        std::vector<I> perm;
+        for (size_type b = 0; b < na; ++b) {
+            const I r0 = block_ptrs_[b];
+            const size_type bs = static_cast<size_type>(block_ptrs_[b + 1] - r0);
+            blk.assign(bs * bs, zero<V>());   // row-major work copy
+            for (size_type i = 0; i < bs; ++i)
+                for (I k = rp[r0 + i]; k < rp[r0 + i + 1]; ++k)
+                    if (ci[k] >= r0 && ci[k] < r0 + static_cast<I>(bs))
+                        blk[i * bs + (ci[k] - r0)] = va[k];
+            perm.resize(bs);
+            for (size_type i = 0; i < bs; ++i) perm[i] = static_cast<I>(i);
+            for (size_type k = 0; k < bs; ++k) {
+                size_type cp = k;   // choose_pivot: first row of maximal magnitude in column k
+                for (size_type i = k + 1; i < bs; ++i)
+                    if (std::abs(blk[cp * bs + k]) < std::abs(blk[i * bs + k])) cp = i;
+                for (size_type j = 0; j < bs; ++j) std::swap(blk[k * bs + j], blk[cp * bs + j]);
+                std::swap(perm[k], perm[cp]);
+                // apply_gauss_jordan_transform(k, k)
+                const V d = blk[k * bs + k];
+                for (size_type i = 0; i < bs; ++i) blk[i * bs + k] /= -d;
+                blk[k * bs + k] = zero<V>();
+                for (size_type i = 0; i < bs; ++i)
+                    for (size_type j = 0; j < bs; ++j)
+                        blk[i * bs + j] += blk[i * bs + k] * blk[k * bs + j];
+                for (size_type j = 0; j < bs; ++j) blk[k * bs + j] /= d;
+                blk[k * bs + k] = one<V>() / d;
+            }
+            // undo the row permutation on the columns and store column-major
+            V *out = blocks_.data() + block_off_[b];
+            for (size_type i = 0; i < bs; ++i)
+                for (size_type j = 0; j < bs; ++j) out[perm[j] * bs + i] = blk[i * bs + j];
+        }
     }
     void apply_impl(const LinOp *b, LinOp *x) const override
     {
         auto bb = as<matrix::Dense<V>>(b);
         auto xx = as<matrix::Dense<V>>(x);
-        for (size_type r = 0; r < size_[0]; ++r)
-            for (size_type c = 0; c < xx->get_size()[1]; ++c) xx->at(r, c) = inv_diag_[r] * bb->at(r, c);
+        const size_type nb = block_ptrs_.size() - 1;
+        for (size_type blk = 0; blk < nb; ++blk) {
+            const size_type r0 = static_cast<size_type>(block_ptrs_[blk]);
+            const size_type bs = static_cast<size_type>(block_ptrs_[blk + 1]) - r0;
+            const V *inv = blocks_.data() + block_off_[blk];
+            for (size_type c = 0; c < xx->get_size()[1]; ++c) {
+                for (size_type i = 0; i < bs; ++i) xx->at(r0 + i, c) = zero<V>();
+                for (size_type inner = 0; inner < bs; ++inner)
+                    for (size_type i = 0; i < bs; ++i)
+                        xx->at(r0 + i, c) += inv[inner * bs + i] * bb->at(r0 + inner, c);
+            }
+        }
     }
     void apply_impl(const LinOp *, const LinOp *, const LinOp *, LinOp *) const override
     {
         throw NotSupported("advanced Jacobi::apply");
     }
-    std::vector<V> inv_diag_;
+    std::vector<I> block_ptrs_;
+    std::vector<size_type> block_off_;
+    std::vector<V> blocks_;
 };
 
-// declared so that solve.cpp:513-556, 598-638 compile; generating one throws
-#define GKO_SHIM_UNSUPPORTED_LINOP(Name, what)                                                 \
-    class Name : public LinOp {                                                                \
-    public:                                                                                    \
-        class Factory;                                                                         \
-        struct parameters_type {                                                               \
-            GKO_SHIM_ON(Factory)                                                               \
-        };                                                                                     \
-        class Factory : public LinOpFactory {                                                  \
-        public:                                                                                \
-            Factory(std::shared_ptr<const Executor> e, const parameters_type &)                \
-                : LinOpFactory(std::move(e))                                                   \
-            {}                                                                                 \
-            std::unique_ptr<LinOp> generate(std::shared_ptr<const LinOp>) const                \
-            {                                                                                  \
-                throw NotSupported(what);                                                      \
-            }                                                                                  \
-                                                                                               \
-        protected:                                                                             \
-            std::unique_ptr<LinOp> generate_impl(std::shared_ptr<const LinOp>) const override  \
-            {                                                                                  \
-                throw NotSupported(what);                                                      \
-            }                                                                                  \
-        };                                                                                     \
-        static parameters_type build() { return {}; }                                          \
-                                                                                               \
-    protected:                                                                                 \
-        Name() : LinOp(nullptr) {}                                                             \
-        void apply_impl(const LinOp *, LinOp *) const override {}                              \
-        void apply_impl(const LinOp *, const LinOp *, const LinOp *, LinOp *) const override {} \
-    }
+// ISAI of a triangular factor [upstream-memory, isai::generate_tri_inverse on the reference
+// executor, sparsity_power = 1]: row i of the approximate inverse M has the pattern J of row
+// i of the factor T and solves (M T)(i, J) = e_i(J) through the dense |J| x |J| system
+// T(J, J)^T m = e.  Applying it is one SpMV.
+template <typename V, typename I, bool Lower>
+class IsaiBase : public LinOp {
+public:
+    std::shared_ptr<const matrix::Csr<V, I>> get_approximate_inverse() const { return inv_; }
 
-template <typename V = default_precision, typename I = int32>
-GKO_SHIM_UNSUPPORTED_LINOP(LowerIsai, "ISAI preconditioner");
-template <typename V = default_precision, typename I = int32>
-GKO_SHIM_UNSUPPORTED_LINOP(UpperIsai, "ISAI preconditioner");
+protected:
+    IsaiBase(std::shared_ptr<const Executor> e, std::shared_ptr<const LinOp> op)
+        : LinOp(e, op->get_size())
+    {
+        auto T0 = as<matrix::Csr<V, I>>(op.get());
+        auto T = matrix::Csr<V, I>::create(e);
+        T->copy_from(T0);
+        T->sort_by_column_index();
+        auto M = matrix::Csr<V, I>::create(e);
+        M->copy_from(T.get());
+        const size_type n = T->get_size()[0];
+        const I *rp = T->get_const_row_ptrs();
+        const I *ci = T->get_const_col_idxs();
+        const V *tv = T->get_const_values();
+        V *mv = M->get_values();
+        std::vector<V> tri, rhs;
+        for (size_type row = 0; row < n; ++row) {
+            const I b = rp[row];
+            const int sz = static_cast<int>(rp[row + 1] - b);
+            tri.assign(static_cast<size_t>(sz) * sz, zero<V>());
+            for (int i = 0; i < sz; ++i) {
+                const I r2 = ci[b + i];
+                I ka = rp[r2], kb = b;   // forall_matching(row r2 of T, pattern)
+                while (ka < rp[r2 + 1] && kb < rp[row + 1]) {
+                    if (ci[ka] == ci[kb]) {
+                        tri[static_cast<size_t>(i) * sz + (kb - b)] = tv[ka];
+                        ++ka;
+                        ++kb;
+                    } else if (ci[ka] < ci[kb]) {
+                        ++ka;
+                    } else {
+                        ++kb;
+                    }
+                }
+            }
+            rhs.assign(sz, zero<V>());
+            if (sz > 0) {
+                if (Lower) {
+                    rhs[sz - 1] = one<V>();
+                    for (int col = sz - 1; col >= 0; --col) {
+                        const V bot = rhs[col] / tri[static_cast<size_t>(col) * sz + col];
+                        rhs[col] = bot;
+                        for (int r = col - 1; r >= 0; --r)
+                            rhs[r] -= bot * tri[static_cast<size_t>(col) * sz + r];
+                    }
+                } else {
+                    rhs[0] = one<V>();
+                    for (int col = 0; col < sz; ++col) {
+                        const V top = rhs[col] / tri[static_cast<size_t>(col) * sz + col];
+                        rhs[col] = top;
+                        for (int r = col + 1; r < sz; ++r)
+                            rhs[r] -= top * tri[static_cast<size_t>(col) * sz + r];
+                    }
+                }
+            }
+            bool finite = true;
+            for (int i = 0; i < sz; ++i) finite = finite && std::isfinite(rhs[i]);
+            for (int i = 0; i < sz; ++i)
+                mv[b + i] = finite ? rhs[i]
+                                   : (static_cast<size_type>(ci[b + i]) == row ? one<V>() : zero<V>());
+        }
+        inv_ = std::move(M);
+    }
+    void apply_impl(const LinOp *b, LinOp *x) const override { inv_->apply(b, x); }
+    void apply_impl(const LinOp *alpha, const LinOp *b, const LinOp *beta, LinOp *x) const override
+    {
+        inv_->apply(alpha, b, beta, x);
+    }
+    std::shared_ptr<matrix::Csr<V, I>> inv_;
+};
+
+#define GKO_SHIM_ISAI(Name, lower)                                                          \
+    template <typename V = default_precision, typename I = int32>                           \
+    class Name : public IsaiBase<V, I, lower> {                                             \
+    public:                                                                                 \
+        class Factory;                                                                      \
+        struct parameters_type {                                                            \
+            GKO_SHIM_ON(Factory)                                                            \
+        };                                                                                  \
+        class Factory : public LinOpFactory {                                               \
+        public:                                                                             \
+            Factory(std::shared_ptr<const Executor> e, const parameters_type &)             \
+                : LinOpFactory(std::move(e))                                                \
+            {}                                                                              \
+            std::unique_ptr<Name> generate(std::shared_ptr<const LinOp> op) const           \
+            {                                                                               \
+                return std::unique_ptr<Name>(new Name(exec_, std::move(op)));               \
+            }                                                                               \
+                                                                                            \
+        protected:                                                                          \
+            std::unique_ptr<LinOp> generate_impl(std::shared_ptr<const LinOp> op) const override \
+            {                                                                               \
+                return generate(std::move(op));                                             \
+            }                                                                               \
+        };                                                                                  \
+        static parameters_type build() { return {}; }                                       \
+                                                                                            \
+    protected:                                                                              \
+        Name(std::shared_ptr<const Executor> e, std::shared_ptr<const LinOp> op)            \
+            : IsaiBase<V, I, lower>(std::move(e), std::move(op))                            \
+        {}                                                                                  \
+    }
+GKO_SHIM_ISAI(LowerIsai, true);
+GKO_SHIM_ISAI(UpperIsai, false);
+
+// Ilu<LSolve, USolve>: x = USolve(LSolve(b)).  Generated from a ParIlu result, or from a plain
+// matrix (then ParILU is run first, as upstream does for a non-composition operand).
 template <typename L, typename U, bool ReverseApply = false, typename I = int32>
-GKO_SHIM_UNSUPPORTED_LINOP(Ilu, "ILU preconditioner");
+class Ilu : public LinOp {
+public:
+    class Factory;
+    struct parameters_type {
+        GKO_SHIM_ON(Factory)
+    };
+    class Factory : public LinOpFactory {
+    public:
+        Factory(std::shared_ptr<const Executor> e, const parameters_type &)
+            : LinOpFactory(std::move(e))
+        {}
+        std::unique_ptr<Ilu> generate(std::shared_ptr<const LinOp> op) const
+        {
+            return std::unique_ptr<Ilu>(new Ilu(exec_, std::move(op)));
+        }
+
+    protected:
+        std::unique_ptr<LinOp> generate_impl(std::shared_ptr<const LinOp> op) const override
+        {
+            return generate(std::move(op));
+        }
+    };
+    static parameters_type build() { return {}; }
+    std::shared_ptr<const L> get_l_solver() const { return l_solver_; }
+    std::shared_ptr<const U> get_u_solver() const { return u_solver_; }
+
+protected:
+    using V = default_precision;
+    Ilu(std::shared_ptr<const Executor> e, std::shared_ptr<const LinOp> op)
+        : LinOp(e, op->get_size())
+    {
+        static_assert(!ReverseApply, "reverse apply is not used by the reference");
+        auto fact = std::dynamic_pointer_cast<const factorization::ParIlu<V, I>>(op);
+        if (!fact)
+            fact = std::shared_ptr<const factorization::ParIlu<V, I>>(
+                factorization::ParIlu<V, I>::build().on(e)->generate(op));
+        l_solver_ = std::shared_ptr<const L>(L::build().on(e)->generate(fact->get_l_factor()));
+        u_solver_ = std::shared_ptr<const U>(U::build().on(e)->generate(fact->get_u_factor()));
+    }
+    void apply_impl(const LinOp *b, LinOp *x) const override
+    {
+        auto bb = as<matrix::Dense<V>>(b);
+        auto tmp = matrix::Dense<V>::create(exec_, bb->get_size());
+        l_solver_->apply(b, tmp.get());
+        u_solver_->apply(tmp.get(), x);
+    }
+    void apply_impl(const LinOp *, const LinOp *, const LinOp *, LinOp *) const override
+    {
+        throw NotSupported("advanced Ilu::apply");
+    }
+    std::shared_ptr<const L> l_solver_;
+    std::shared_ptr<const U> u_solver_;
+};
 
 }  // namespace preconditioner
-
-namespace factorization {
-template <typename V = default_precision, typename I = int32>
-GKO_SHIM_UNSUPPORTED_LINOP(ParIlu, "ParILU factorization");
-}  // namespace factorization
 
 // ---------------------------------------------------------------------------- solvers
 namespace solver {

@@ -377,4 +377,135 @@ int ref_iterate(void *h, int rank, int k, double *out, int64_t cap)
 {
     return copy_out(static_cast<Run *>(h)->ranks[rank].iterates[k], out, cap);
 }
+
+// ---- kernel-level probes: the Ginkgo stand-in's local solvers and preconditioners, built
+// with exactly the builder calls of source/solve.cpp:469-652, on a caller-supplied CSR ----
+struct RefPrecond {
+    std::shared_ptr<gko::Executor> exec;
+    std::shared_ptr<gko::matrix::Csr<VT, IT>> A;
+    std::shared_ptr<const gko::LinOp> op;
+    std::string kind;
+};
+
+static std::shared_ptr<gko::matrix::Csr<VT, IT>> make_csr(std::shared_ptr<gko::Executor> exec,
+                                                          int n, const int32_t *rp,
+                                                          const int32_t *ci, const double *v)
+{
+    auto A = gko::matrix::Csr<VT, IT>::create(exec, gko::dim<2>(n, n), rp[n]);
+    std::copy(rp, rp + n + 1, A->get_row_ptrs());
+    std::copy(ci, ci + rp[n], A->get_col_idxs());
+    std::copy(v, v + rp[n], A->get_values());
+    return std::shared_ptr<gko::matrix::Csr<VT, IT>>(std::move(A));
+}
+
+void *ref_precond_create(int n, const int32_t *rp, const int32_t *ci, const double *v,
+                         const char *kind, int max_block_size)
+{
+    auto *p = new RefPrecond();
+    p->exec = gko::ReferenceExecutor::create();
+    p->A = make_csr(p->exec, n, rp, ci, v);
+    p->kind = kind;
+    auto exec = p->exec;
+    if (p->kind == "block-jacobi") {   // solve.cpp:496-505
+        using bj = gko::preconditioner::Jacobi<VT, IT>;
+        p->op = gko::share(bj::build().with_max_block_size(max_block_size).on(exec)->generate(p->A));
+    } else if (p->kind == "ilu") {     // solve.cpp:513-526
+        auto par_ilu = gko::factorization::ParIlu<VT, IT>::build().on(exec)->generate(p->A);
+        auto f = gko::preconditioner::Ilu<gko::solver::LowerTrs<VT, IT>,
+                                          gko::solver::UpperTrs<VT, IT>, false>::build()
+                     .on(exec);
+        p->op = gko::share(f->generate(gko::share(par_ilu)));
+    } else if (p->kind == "isai") {    // solve.cpp:540-549
+        using LowerIsai = gko::preconditioner::LowerIsai<VT, IT>;
+        using UpperIsai = gko::preconditioner::UpperIsai<VT, IT>;
+        auto f = gko::preconditioner::Ilu<LowerIsai, UpperIsai, false, IT>::build().on(exec);
+        p->op = gko::share(f->generate(p->A));
+    }
+    return p;
+}
+void ref_precond_free(void *h) { delete static_cast<RefPrecond *>(h); }
+void ref_precond_apply(void *h, const double *b, double *x)
+{
+    auto *p = static_cast<RefPrecond *>(h);
+    const auto n = p->A->get_size()[0];
+    auto bb = gko::matrix::Dense<VT>::create(p->exec, gko::dim<2>(n, 1));
+    auto xx = gko::matrix::Dense<VT>::create(p->exec, gko::dim<2>(n, 1));
+    std::copy(b, b + n, bb->get_values());
+    p->op->apply(bb.get(), xx.get());
+    std::copy(xx->get_const_values(), xx->get_const_values() + n, x);
+}
+int ref_precond_block_ptrs(void *h, int32_t *out, int64_t cap)
+{
+    auto *p = static_cast<RefPrecond *>(h);
+    auto j = dynamic_cast<const gko::preconditioner::Jacobi<VT, IT> *>(p->op.get());
+    if (!j) return -1;
+    return copy_out(j->get_block_pointers(), out, cap);
+}
+int ref_precond_blocks(void *h, double *out, int64_t cap)
+{
+    auto *p = static_cast<RefPrecond *>(h);
+    auto j = dynamic_cast<const gko::preconditioner::Jacobi<VT, IT> *>(p->op.get());
+    if (!j) return -1;
+    return copy_out(j->get_blocks(), out, cap);
+}
+// which: 0 L, 1 U (ILU factors); 2 approximate inverse of L, 3 of U (ISAI).  rp == NULL: nnz
+int64_t ref_precond_csr(void *h, int which, int32_t *rp, int32_t *ci, double *v)
+{
+    auto *p = static_cast<RefPrecond *>(h);
+    std::shared_ptr<const gko::matrix::Csr<VT, IT>> m;
+    using TrsIlu = gko::preconditioner::Ilu<gko::solver::LowerTrs<VT, IT>,
+                                            gko::solver::UpperTrs<VT, IT>, false>;
+    using IsaiIlu = gko::preconditioner::Ilu<gko::preconditioner::LowerIsai<VT, IT>,
+                                             gko::preconditioner::UpperIsai<VT, IT>, false, IT>;
+    if (auto t = dynamic_cast<const TrsIlu *>(p->op.get())) {
+        if (which == 0) m = t->get_l_solver()->get_system_matrix();
+        if (which == 1) m = t->get_u_solver()->get_system_matrix();
+    } else if (auto s = dynamic_cast<const IsaiIlu *>(p->op.get())) {
+        if (which == 2) m = s->get_l_solver()->get_approximate_inverse();
+        if (which == 3) m = s->get_u_solver()->get_approximate_inverse();
+    }
+    if (!m) return -1;
+    const auto n = m->get_size()[0];
+    const int64_t nnz = m->get_const_row_ptrs()[n];
+    if (rp) {
+        std::copy(m->get_const_row_ptrs(), m->get_const_row_ptrs() + n + 1, rp);
+        std::copy(m->get_const_col_idxs(), m->get_const_col_idxs() + nnz, ci);
+        std::copy(m->get_const_values(), m->get_const_values() + nnz, v);
+    }
+    return nnz;
+}
+// Cg / Gmres(restart) with Combined(Iteration(max_iters), ResidualNormReduction(tol)) and an
+// optional preconditioner handle, x = warm start in, solution out (solve.cpp:469-478, 572-652)
+void ref_krylov_solve(int n, const int32_t *rp, const int32_t *ci, const double *v,
+                      const double *b, double *x, int gmres, int restart, int max_iters,
+                      double tol, void *precond)
+{
+    auto exec = gko::ReferenceExecutor::create();
+    auto A = make_csr(exec, n, rp, ci, v);
+    auto crit = gko::share(
+        gko::stop::Combined::build()
+            .with_criteria(gko::stop::Iteration::build().with_max_iters(max_iters).on(exec),
+                           gko::stop::ResidualNormReduction<VT>::build()
+                               .with_reduction_factor(tol)
+                               .on(exec))
+            .on(exec));
+    std::shared_ptr<const gko::LinOp> pre;
+    if (precond) pre = static_cast<RefPrecond *>(precond)->op;
+    std::shared_ptr<gko::LinOp> solver;
+    if (gmres) {
+        auto b_ = gko::solver::Gmres<VT>::build().with_criteria(crit).with_krylov_dim(restart);
+        if (pre) b_.with_generated_preconditioner(pre);
+        solver = gko::share(b_.on(exec)->generate(A));
+    } else {
+        auto b_ = gko::solver::Cg<VT>::build().with_criteria(crit);
+        if (pre) b_.with_generated_preconditioner(pre);
+        solver = gko::share(b_.on(exec)->generate(A));
+    }
+    auto bb = gko::matrix::Dense<VT>::create(exec, gko::dim<2>(n, 1));
+    auto xx = gko::matrix::Dense<VT>::create(exec, gko::dim<2>(n, 1));
+    std::copy(b, b + n, bb->get_values());
+    std::copy(x, x + n, xx->get_values());
+    solver->apply(bb.get(), xx.get());
+    std::copy(xx->get_const_values(), xx->get_const_values() + n, x);
+}
 }
