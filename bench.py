@@ -49,6 +49,9 @@ def parse():
                     help="one-sided Put exchange + decentralised convergence flags (cfg4)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-breakdown", action="store_true",
+                    help="diagnostic: synchronise between upload / run / download of the e2e leg "
+                         "and report the three wall times (changes the e2e number slightly)")
     return ap.parse_args()
 
 
@@ -361,9 +364,21 @@ def main():
         for s in subs:
             s.upload_rhs(rhs.data_ptr())
             s.reset()
+        if args.e2e_breakdown:
+            for s in subs:
+                s.sync()
+            t_up = time.perf_counter() - t0
         r2 = run_steps(args.steps)
+        if args.e2e_breakdown:
+            for s in subs:
+                s.sync()
+            t_run = time.perf_counter() - t0
         for s in subs:
             s.download_solution(sol.data_ptr())
+        if args.e2e_breakdown:
+            for s in subs:
+                s.sync()
+            t_down = time.perf_counter() - t0
         barrier()
         te = time.perf_counter() - t0
         if world > 1:
@@ -382,6 +397,10 @@ def main():
                "note": "schwz_b200_ras_upload_rhs + ras_reset + ras_run(K) + "
                        "ras_download_solution with pinned host buffers; rhs/solution copies "
                        "amortised over the K steps, residual norms read back every step"}
+        if args.e2e_breakdown:
+            e2e["breakdown_ms_rank0"] = {"upload+reset": 1e3 * t_up, "run": 1e3 * (t_run - t_up),
+                                         "download": 1e3 * (t_down - t_run),
+                                         "final_barrier": 1e3 * (te - t_down)}
 
     # ---- CPU baseline beside it (rank 0, N == 1 only) ------------------------
     cpu = None

@@ -31,6 +31,7 @@ typedef struct schwz_csr schwz_csr;         /* device CSR matrix                
 typedef struct schwz_cg schwz_cg;           /* device-resident CG workspace       */
 typedef struct schwz_gmres schwz_gmres;     /* device-resident GMRES(m) workspace */
 typedef struct schwz_trs schwz_trs;         /* level-scheduled triangular solve   */
+typedef struct schwz_precond schwz_precond; /* local preconditioner of CG / GMRES */
 typedef struct schwz_setup schwz_setup;     /* host index sets of one problem     */
 typedef struct schwz_ras schwz_ras;         /* one subdomain of the RAS iteration */
 typedef struct schwz_comm schwz_comm;       /* NCCL communicator (residual-norm allgather only) */
@@ -120,6 +121,36 @@ int schwz_b200_gmres_solve(schwz_gmres *g, const double *dev_b, double *dev_x,
 int schwz_b200_gmres_result(schwz_gmres *g, int32_t *iters, double *resnorm,
                             double *resnorm0);
 
+/* ---- local preconditioners of the iterative local solve ------------------------
+ * replaces: gko::preconditioner::Jacobi(max_block_size), gko::factorization::ParIlu +
+ * gko::preconditioner::Ilu<LowerTrs, UpperTrs>, gko::preconditioner::Ilu<LowerIsai,
+ * UpperIsai> as built at source/solve.cpp:496-505, 513-532, 540-556 (GMRES) and
+ * :581-589, 598-617, 625-638 (CG); metadata.local_precond / precond_max_block_size
+ * (include/settings.hpp, --local_precond / --precond_max_block_size of bench_ras).
+ * kind: 1 block-jacobi, 2 ilu, 3 isai.  Generated on the host from the host CSR of the
+ * local matrix (setup), applied on the device (every Krylov iteration).  apply: z = M^-1 r,
+ * optionally *dev_dot = r.z.  The getters return host copies of what was generated
+ * (block pointers; inverse blocks column-major; which = 0 L, 1 U, 2 ISAI(L), 3 ISAI(U));
+ * pass NULL to query the length.  ctx == NULL generates a host-only handle (no device, no
+ * apply) - used to check the generation without a GPU. */
+enum { SCHWZ_PRECOND_NONE = 0, SCHWZ_PRECOND_BLOCK_JACOBI = 1, SCHWZ_PRECOND_ILU = 2,
+       SCHWZ_PRECOND_ISAI = 3 };
+int schwz_b200_precond_create(schwz_ctx *ctx, int32_t n, const int32_t *host_rowptr,
+                              const int32_t *host_col, const double *host_val, int32_t kind,
+                              int32_t max_block_size, schwz_precond **out);
+int schwz_b200_precond_destroy(schwz_precond *p);
+int schwz_b200_precond_apply(schwz_precond *p, const double *dev_r, double *dev_z,
+                             double *dev_dot_or_null);
+int64_t schwz_b200_precond_bytes_per_apply(schwz_precond *p);
+int64_t schwz_b200_precond_block_ptrs(schwz_precond *p, int32_t *host_out);
+int64_t schwz_b200_precond_blocks(schwz_precond *p, double *host_out);
+int64_t schwz_b200_precond_csr(schwz_precond *p, int32_t which, int32_t *host_rowptr,
+                               int32_t *host_col, double *host_val);
+/* with_preconditioner / with_generated_preconditioner of the solver factories; NULL detaches.
+ * The preconditioner must outlive the solver. */
+int schwz_b200_cg_set_precond(schwz_cg *cg, schwz_precond *p);
+int schwz_b200_gmres_set_precond(schwz_gmres *g, schwz_precond *p);
+
 /* ---- factorised direct variant ----------------------------------------------
  * replaces: gko::solver::LowerTrs / UpperTrs generate+apply and
  * gko::matrix::Permutation::apply (source/solve.cpp:391-399, 717-720;
@@ -207,6 +238,8 @@ typedef struct {
     int32_t overlap;
     int32_t use_mixed_precision; /* settings.use_mixed_precision, MixedValueType = float: halo
                                   * values travel as floats (restricted_schwarz.cpp:483-603) */
+    int32_t local_precond;       /* metadata.local_precond: SCHWZ_PRECOND_* (iterative only) */
+    int32_t precond_max_block_size; /* metadata.precond_max_block_size (block-jacobi)        */
 } schwz_ras_options;
 
 int schwz_b200_ras_create(schwz_ctx *ctx, schwz_setup *s, int32_t rank,

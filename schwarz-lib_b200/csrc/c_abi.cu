@@ -14,6 +14,11 @@ struct schwz_ctx { Ctx impl; explicit schwz_ctx(int d) : impl(d) {} };
 struct schwz_csr { std::unique_ptr<DeviceCsr> impl; };
 struct schwz_cg { std::unique_ptr<CgSolver> impl; };
 struct schwz_gmres { std::unique_ptr<GmresSolver> impl; };
+struct schwz_precond {
+    std::unique_ptr<Preconditioner> impl;   // null for a host-only handle (ctx == NULL)
+    PrecondData host_only;
+    const PrecondData &data() const { return impl ? impl->host : host_only; }
+};
 struct schwz_trs { std::unique_ptr<TrsPlan> impl; };
 struct schwz_setup { std::unique_ptr<Setup> impl; };
 struct schwz_ras { std::unique_ptr<Ras> impl; };
@@ -284,6 +289,76 @@ int schwz_b200_cg_result(schwz_cg *cg, int32_t *iters, double *resnorm, double *
     cg->impl->result(iters, resnorm, resnorm0);
     ABI_END
 }
+// ---- local preconditioners ------------------------------------------------------
+int schwz_b200_precond_create(schwz_ctx *ctx, int32_t n, const int32_t *rp, const int32_t *ci,
+                              const double *v, int32_t kind, int32_t max_block_size,
+                              schwz_precond **out)
+{
+    ABI_BEGIN
+    auto *h = new schwz_precond();
+    if (ctx)
+        h->impl.reset(new Preconditioner(ctx->impl, n, rp, ci, v, kind, max_block_size));
+    else
+        h->host_only.generate(n, rp, ci, v, kind, max_block_size);
+    *out = h;
+    ABI_END
+}
+int schwz_b200_precond_destroy(schwz_precond *p)
+{
+    ABI_BEGIN
+    delete p;
+    ABI_END
+}
+int schwz_b200_precond_apply(schwz_precond *p, const double *dev_r, double *dev_z,
+                             double *dev_dot_or_null)
+{
+    ABI_BEGIN
+    SCHWZ_REQUIRE(p->impl != nullptr, "host-only preconditioner handle (created without a context)");
+    p->impl->apply(dev_r, dev_z, dev_dot_or_null, nullptr);
+    ABI_END
+}
+int64_t schwz_b200_precond_bytes_per_apply(schwz_precond *p)
+{
+    return p->impl ? p->impl->bytes_per_apply() : 0;
+}
+int64_t schwz_b200_precond_block_ptrs(schwz_precond *p, int32_t *host_out)
+{
+    const auto &bp = p->data().block_ptrs;
+    if (host_out) std::copy(bp.begin(), bp.end(), host_out);
+    return (int64_t)bp.size();
+}
+int64_t schwz_b200_precond_blocks(schwz_precond *p, double *host_out)
+{
+    const auto &b = p->data().blocks;
+    if (host_out) std::copy(b.begin(), b.end(), host_out);
+    return (int64_t)b.size();
+}
+int64_t schwz_b200_precond_csr(schwz_precond *p, int32_t which, int32_t *rp, int32_t *ci, double *v)
+{
+    const PrecondData &M = p->data();
+    const HostCsr &T = which == 0 ? M.L : which == 1 ? M.U : which == 2 ? M.Li : M.Ui;
+    if (rp) {
+        std::copy(T.rp.begin(), T.rp.end(), rp);
+        std::copy(T.ci.begin(), T.ci.end(), ci);
+        std::copy(T.v.begin(), T.v.end(), v);
+    }
+    return (int64_t)T.ci.size();
+}
+int schwz_b200_cg_set_precond(schwz_cg *cg, schwz_precond *p)
+{
+    ABI_BEGIN
+    SCHWZ_REQUIRE(!p || p->impl, "host-only preconditioner handle");
+    cg->impl->set_precond(p ? p->impl.get() : nullptr);
+    ABI_END
+}
+int schwz_b200_gmres_set_precond(schwz_gmres *g, schwz_precond *p)
+{
+    ABI_BEGIN
+    SCHWZ_REQUIRE(!p || p->impl, "host-only preconditioner handle");
+    g->impl->set_precond(p ? p->impl.get() : nullptr);
+    ABI_END
+}
+
 int schwz_b200_gmres_create(schwz_ctx *ctx, const schwz_csr *A, int32_t restart, schwz_gmres **out)
 {
     ABI_BEGIN
@@ -566,6 +641,8 @@ int schwz_b200_ras_create(schwz_ctx *ctx, schwz_setup *s, int32_t rank, const do
     ro.restart_iter = o->restart_iter;
     ro.overlap = o->overlap;
     ro.use_mixed_precision = o->use_mixed_precision;
+    ro.local_precond = o->local_precond;
+    ro.precond_max_block_size = o->precond_max_block_size;
     auto *h = new schwz_ras();
     h->impl.reset(new Ras(ctx->impl, *s->impl, rank, rhs, ro));
     *out = h;

@@ -111,7 +111,7 @@ void launch_cg_init(const Ctx &ctx, CgScalars *s, int32_t max_iters, double tol,
                     const int32_t *outer_stop);
 void launch_cg_p_update(const Ctx &ctx, int64_t n, const double *r, double *p, const CgScalars *s);
 void launch_cg_xr_update(const Ctx &ctx, int64_t n, double *x, double *r, const double *p,
-                         const double *q, CgScalars *s);
+                         const double *q, CgScalars *s, bool precond = false);
 
 // halo
 void launch_halo_pack_push(const Ctx &ctx, int32_t nseg, const int32_t *seg_off_dev,

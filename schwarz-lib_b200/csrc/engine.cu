@@ -229,6 +229,15 @@ Ras::Ras(const Ctx &ctx_, Setup &setup, int32_t rank_, const double *host_rhs_gl
     if (opt.local_solver == 2) {
         if (opt.non_symmetric) gmres.reset(new GmresSolver(ctx, *A, opt.restart_iter));
         else cg.reset(new CgSolver(ctx, *A));
+        if (opt.local_precond != PRECOND_NONE) {
+            // solve.cpp:486-652: generated once from the local matrix, before the loop
+            precond.reset(new Preconditioner(ctx, R.local.nrows, R.local.rp.data(),
+                                             R.local.ci.data(), R.local.v.data(),
+                                             opt.local_precond, opt.precond_max_block_size));
+            precond->release_host();
+            if (gmres) gmres->set_precond(precond.get());
+            else cg->set_precond(precond.get());
+        }
     }
     ctx.sync();
 }

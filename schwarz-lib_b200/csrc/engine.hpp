@@ -32,11 +32,53 @@ void launch_gmres_small(const Ctx &ctx, const DeviceCsr &A, const double *b, dou
                         int32_t m, int32_t max_iters, double tol, double *resnorm_out,
                         double *r0_out, int32_t *total_out);
 
+// ---- local preconditioners (source/solve.cpp:486-652; precond.cu) --------------
+class TrsPlan;
+enum PrecondKind { PRECOND_NONE = 0, PRECOND_BLOCK_JACOBI = 1, PRECOND_ILU = 2, PRECOND_ISAI = 3 };
+
+// what generation produces (host; setup time)
+struct PrecondData {
+    std::vector<int32_t> block_ptrs;   // block-Jacobi: block b = rows [block_ptrs[b], block_ptrs[b+1])
+    std::vector<int64_t> block_off;    //   offset of its inverse in `blocks`
+    std::vector<double> blocks;        //   inverse diagonal blocks, column-major, ld = block size
+    HostCsr L, U, Li, Ui;              // ILU(0) factors and their sparse approximate inverses
+    void generate(int32_t n, const int32_t *rp, const int32_t *ci, const double *v, int32_t kind,
+                  int32_t max_block_size);
+};
+
+class Preconditioner {
+public:
+    // host CSR of the local matrix; generation happens here (setup time)
+    Preconditioner(const Ctx &ctx, int32_t n, const int32_t *rp, const int32_t *ci,
+                   const double *v, int32_t kind, int32_t max_block_size);
+    ~Preconditioner();
+    // z = M^-1 r on ctx.stream; dot_result (device, optional) <- r.z; the launches are
+    // no-ops when *stop != 0
+    void apply(const double *r, double *z, double *dot_result, const int32_t *stop);
+    int32_t kind() const { return kind_; }
+    int32_t size() const { return n_; }
+    int64_t bytes_per_apply() const;
+    void release_host();   // drop the host copy below (large subdomains)
+    PrecondData host;      // what was generated (parity tests read it through the C ABI)
+
+private:
+    const Ctx &ctx_;
+    int32_t n_, kind_;
+    int64_t inv_bytes_ = 0;
+    int32_t *dev_block_ptrs_ = nullptr, *dev_row_block_ = nullptr;
+    int64_t *dev_block_off_ = nullptr;
+    double *dev_blocks_ = nullptr, *tmp_ = nullptr, *in_ = nullptr;
+    std::unique_ptr<TrsPlan> Ltrs_, Utrs_;
+    std::unique_ptr<DeviceCsr> dev_Li_, dev_Ui_;
+};
+
 // ---- CG (Ginkgo Cg semantics; source/solve.cpp:469-478, 572-652, 746-754) ----
 class CgSolver {
 public:
     CgSolver(const Ctx &ctx, const DeviceCsr &A);
     ~CgSolver();
+    // z = M^-1 r ; rho = r.z ; p = z + (rho/prev_rho) p  (with_preconditioner, :581-638)
+    void set_precond(Preconditioner *M);
     // x holds the warm start; asynchronous on ctx.stream.  outer_stop: optional
     // device flag that turns the whole solve into a no-op.
     void solve(const double *b, double *x, int32_t max_iters, double tol,
@@ -50,7 +92,8 @@ private:
     const Ctx &ctx_;
     const DeviceCsr &A_;
     int64_t n_;
-    double *r_ = nullptr, *p_ = nullptr, *q_ = nullptr;
+    double *r_ = nullptr, *p_ = nullptr, *q_ = nullptr, *z_ = nullptr;
+    Preconditioner *M_ = nullptr;
     CgScalars *s_ = nullptr;
     int32_t *pinned_stop_ = nullptr;   // 2 slots
     cudaEvent_t ev_[2] = {nullptr, nullptr};
@@ -61,6 +104,8 @@ class GmresSolver {
 public:
     GmresSolver(const Ctx &ctx, const DeviceCsr &A, int32_t restart);
     ~GmresSolver();
+    // right preconditioning: w = A M^-1 v_k ; x += M^-1 (V y)  (:496-556)
+    void set_precond(Preconditioner *M);
     void solve(const double *b, double *x, int32_t max_iters, double tol);
     void result(int32_t *iters, double *resnorm, double *resnorm0);
 
@@ -71,6 +116,8 @@ private:
     int32_t m_;
     double *V_ = nullptr;    // (m+1) x n basis, row-major by vector
     double *w_ = nullptr;
+    double *pv_ = nullptr, *upd_ = nullptr;   // preconditioned vector, V y (only with M_)
+    Preconditioner *M_ = nullptr;
     double *small_ = nullptr;   // Hessenberg, rotations, g, y and scalars
     int32_t *pinned_stop_ = nullptr;
     cudaEvent_t ev_[2] = {nullptr, nullptr};
@@ -82,7 +129,8 @@ public:
     TrsPlan(const Ctx &ctx, int32_t n, const int32_t *rp, const int32_t *ci, const double *v,
             bool upper);
     ~TrsPlan();
-    void solve(const double *b, double *x);
+    // stop: optional device flag, the launches are no-ops when it is set
+    void solve(const double *b, double *x, const int32_t *stop = nullptr);
     int32_t num_levels() const { return num_levels_; }
     int32_t num_launches() const { return (int32_t)segments_.size(); }
     int64_t nnz() const { return nnz_; }
@@ -109,9 +157,13 @@ private:
     int32_t *chain_rp_ = nullptr, *chain_ci_ = nullptr;   // outside entries, indexed by position
     double *chain_v_ = nullptr, *dinv_ = nullptr, *block_t_ = nullptr;
     int32_t num_blocks_ = 0;
-    cudaGraphExec_t graph_ = nullptr;
-    const double *graph_b_ = nullptr;
-    double *graph_x_ = nullptr;
+    struct Captured {
+        const double *b;
+        double *x;
+        const int32_t *stop;
+        cudaGraphExec_t exec;
+    };
+    std::vector<Captured> graphs_;
 };
 
 struct RasOptions {
@@ -121,6 +173,8 @@ struct RasOptions {
     // settings.use_mixed_precision with MixedValueType = float: halo values travel as floats
     // in the gathered exchanges (restricted_schwarz.cpp:483-603, 769-787, 898-903)
     int32_t use_mixed_precision = 0;
+    // metadata.local_precond / precond_max_block_size (PrecondKind; iterative local solve only)
+    int32_t local_precond = 0, precond_max_block_size = 16;
 };
 
 // Layout of the peer-visible mailbox of a subdomain (byte offsets from base).
@@ -200,6 +254,7 @@ public:
     double *resnorm_dev = nullptr;
     int32_t *num_converged_dev = nullptr, *conv_sent = nullptr;
     std::unique_ptr<DeviceCsr> A, I;
+    std::unique_ptr<Preconditioner> precond;
     std::unique_ptr<CgSolver> cg;
     std::unique_ptr<GmresSolver> gmres;
     std::unique_ptr<TrsPlan> Ltrs, Utrs;

@@ -750,7 +750,7 @@ void launch_cg_p_update(const Ctx &ctx, int64_t n, const double *r, double *p, c
 __global__ void __launch_bounds__(kBlock)
     cg_xr_update_kernel(int64_t n, double *__restrict__ x, double *__restrict__ r,
                         const double *__restrict__ p, const double *__restrict__ q,
-                        CgScalars *s, double *partials, unsigned int *ticket)
+                        CgScalars *s, double *partials, unsigned int *ticket, int precond)
 {
     __shared__ double s_warp[kBlock / 32];
     if (s->stop) return;
@@ -810,7 +810,9 @@ __global__ void __launch_bounds__(kBlock)
         double rho_new = reduce_partials(partials, gridDim.x, s_warp);
         if (threadIdx.x == 0) {
             s->prev_rho = rho;
-            s->rho = rho_new;
+            // with a preconditioner rho = r.z comes from the next M^-1 application and this
+            // sum is only ||r||^2 for the stop test
+            if (!precond) s->rho = rho_new;
             const int it = s->iter + 1;
             s->iter = it;
             const double tau = sqrt(rho_new);
@@ -821,11 +823,11 @@ __global__ void __launch_bounds__(kBlock)
 }
 
 void launch_cg_xr_update(const Ctx &ctx, int64_t n, double *x, double *r, const double *p,
-                         const double *q, CgScalars *s)
+                         const double *q, CgScalars *s, bool precond)
 {
     ctx.use();
     cg_xr_update_kernel<<<vec_grid((n + 1) / 2), kBlock, 0, ctx.stream>>>(
-        n, x, r, p, q, s, ctx.partials, ctx.tickets + 2);
+        n, x, r, p, q, s, ctx.partials, ctx.tickets + 2, precond ? 1 : 0);
     SCHWZ_CUDA(cudaGetLastError());
     count_launch();
 }

@@ -1,0 +1,473 @@
+// Local preconditioners of the iterative local solve.  The reference
+// builds them with Ginkgo factories (source/solve.cpp:486-652):
+//   "block-jacobi"  preconditioner::Jacobi(max_block_size)                 :496-505, :581-589
+//   "ilu"           factorization::ParIlu + preconditioner::Ilu<LowerTrs, UpperTrs> :513-532
+//   "isai"          preconditioner::Ilu<LowerIsai, UpperIsai>              :540-556, :625-638
+// Generation is setup work and runs on the host (same arithmetic sequence as the oracle
+// restatement, which is pinned to the stand-in the reference itself is linked with);
+// application is the per-iteration hot path and runs on the device:
+//   block-Jacobi  one streaming kernel, z = Dinv r with r.z fused (8*bs + 16 B/row)
+//   ILU           two level-scheduled triangular solves (TrsPlan) + a dot
+//   ISAI          two CSR SpMVs with the TMA kernel, r.z fused into the second
+#include <algorithm>
+#include <cmath>
+#include <numeric>
+
+#include "engine.hpp"
+
+namespace schwz_b200 {
+
+// =============================================================================
+// host generation
+// =============================================================================
+namespace {
+
+// jacobi::find_blocks: natural blocks = runs of rows with equal column pattern (at most
+// max_bs rows), merged greedily while the merged size stays <= max_bs.
+void find_blocks(int32_t n, const int32_t *rp, const int32_t *ci, int32_t max_bs,
+                 std::vector<int32_t> &bp)
+{
+    bp.assign(1, 0);
+    if (n == 0) return;
+    std::vector<int32_t> nat_size;
+    int32_t run = 1;
+    for (int32_t i = 1; i < n; ++i) {
+        const int32_t len = rp[i + 1] - rp[i];
+        const bool same = len == rp[i] - rp[i - 1] &&
+                          std::equal(ci + rp[i], ci + rp[i + 1], ci + rp[i - 1]);
+        if (same && run < max_bs) {
+            ++run;
+        } else {
+            nat_size.push_back(run);
+            run = 1;
+        }
+    }
+    nat_size.push_back(run);
+    int32_t acc = nat_size[0];
+    for (size_t k = 1; k < nat_size.size(); ++k) {
+        if (acc + nat_size[k] <= max_bs) {
+            acc += nat_size[k];
+        } else {
+            bp.push_back(bp.back() + acc);
+            acc = nat_size[k];
+        }
+    }
+    bp.push_back(bp.back() + acc);
+}
+
+// in-place Gauss-Jordan inversion with implicit row pivoting; B row-major bs x bs, result
+// written column-major with the pivoting undone
+void invert_block(double *B, int32_t bs, double *out)
+{
+    int32_t perm[32];
+    for (int32_t i = 0; i < bs; ++i) perm[i] = i;
+    for (int32_t k = 0; k < bs; ++k) {
+        int32_t piv = k;
+        for (int32_t i = k + 1; i < bs; ++i)
+            if (std::fabs(B[piv * bs + k]) < std::fabs(B[i * bs + k])) piv = i;
+        if (piv != k) {
+            std::swap_ranges(B + k * bs, B + (k + 1) * bs, B + piv * bs);
+            std::swap(perm[k], perm[piv]);
+        }
+        const double d = B[k * bs + k];
+        for (int32_t i = 0; i < bs; ++i) B[i * bs + k] /= -d;
+        B[k * bs + k] = 0.0;
+        for (int32_t i = 0; i < bs; ++i) {
+            const double f = B[i * bs + k];
+            for (int32_t j = 0; j < bs; ++j) B[i * bs + j] += f * B[k * bs + j];
+        }
+        for (int32_t j = 0; j < bs; ++j) B[k * bs + j] /= d;
+        B[k * bs + k] = 1.0 / d;
+    }
+    for (int32_t i = 0; i < bs; ++i)
+        for (int32_t j = 0; j < bs; ++j) out[(size_t)perm[j] * bs + i] = B[i * bs + j];
+}
+
+void sort_rows(HostCsr &A)
+{
+    std::vector<std::pair<int32_t, double>> row;
+    for (int32_t r = 0; r < A.nrows; ++r) {
+        bool sorted = true;
+        for (int32_t k = A.rp[r] + 1; k < A.rp[r + 1]; ++k) sorted = sorted && A.ci[k - 1] <= A.ci[k];
+        if (sorted) continue;
+        row.clear();
+        for (int32_t k = A.rp[r]; k < A.rp[r + 1]; ++k) row.emplace_back(A.ci[k], A.v[k]);
+        std::stable_sort(row.begin(), row.end(),
+                         [](const auto &a, const auto &b) { return a.first < b.first; });
+        for (size_t k = 0; k < row.size(); ++k) {
+            A.ci[A.rp[r] + k] = row[k].first;
+            A.v[A.rp[r] + k] = row[k].second;
+        }
+    }
+}
+
+// ParILU, reference-executor semantics: unit-diagonal L, U with the diagonal (a zero or
+// missing diagonal entry becomes 1), then one sequential row-major sweep of
+//   l_rc = (a_rc - sum_{k<c} l_rk u_kc) / u_cc   (r > c),   u_rc = a_rc - sum_{k<r} l_rk u_kc
+// which is ILU(0).  The running sum also subtracts the product that contains the unknown and
+// adds it back afterwards - upstream's formulation, visible in the last bit, kept.
+void par_ilu(HostCsr A, HostCsr &L, HostCsr &U)
+{
+    sort_rows(A);
+    const int32_t n = A.nrows;
+    HostCsr D;   // A with an explicit diagonal
+    D.nrows = D.ncols = n;
+    D.rp.assign((size_t)n + 1, 0);
+    D.ci.reserve(A.ci.size() + n);
+    D.v.reserve(A.ci.size() + n);
+    for (int32_t r = 0; r < n; ++r) {
+        bool have = false;
+        for (int32_t k = A.rp[r]; k < A.rp[r + 1]; ++k) {
+            const int32_t c = A.ci[k];
+            if (!have && c > r) {
+                D.ci.push_back(r);
+                D.v.push_back(0.0);
+                have = true;
+            }
+            have = have || c == r;
+            D.ci.push_back(c);
+            D.v.push_back(A.v[k]);
+        }
+        if (!have) {
+            D.ci.push_back(r);
+            D.v.push_back(0.0);
+        }
+        D.rp[r + 1] = (int32_t)D.ci.size();
+    }
+    L = HostCsr();
+    HostCsr Uc;   // U by columns
+    L.nrows = L.ncols = Uc.nrows = Uc.ncols = n;
+    L.rp.assign((size_t)n + 1, 0);
+    Uc.rp.assign((size_t)n + 1, 0);
+    for (int32_t r = 0; r < n; ++r)
+        for (int32_t k = D.rp[r]; k < D.rp[r + 1]; ++k)
+            if (D.ci[k] >= r) Uc.rp[D.ci[k] + 1]++;
+    for (int32_t c = 0; c < n; ++c) Uc.rp[c + 1] += Uc.rp[c];
+    Uc.ci.resize(Uc.rp[n]);
+    Uc.v.resize(Uc.rp[n]);
+    std::vector<int32_t> fill(Uc.rp.begin(), Uc.rp.end() - 1);
+    for (int32_t r = 0; r < n; ++r) {
+        for (int32_t k = D.rp[r]; k < D.rp[r + 1]; ++k) {
+            const int32_t c = D.ci[k];
+            if (c < r) {
+                L.ci.push_back(c);
+                L.v.push_back(D.v[k]);
+            } else {
+                Uc.ci[fill[c]] = r;
+                Uc.v[fill[c]] = (c == r && D.v[k] == 0.0) ? 1.0 : D.v[k];
+                fill[c]++;
+            }
+        }
+        L.ci.push_back(r);
+        L.v.push_back(1.0);
+        L.rp[r + 1] = (int32_t)L.ci.size();
+    }
+    for (int32_t r = 0; r < n; ++r)
+        for (int32_t e = D.rp[r]; e < D.rp[r + 1]; ++e) {
+            const int32_t c = D.ci[e];
+            int32_t a = L.rp[r], b = Uc.rp[c];
+            double s = D.v[e], last = 0.0;
+            while (a < L.rp[r + 1] && b < Uc.rp[c + 1]) {
+                const int32_t ka = L.ci[a], kb = Uc.ci[b];
+                if (ka == kb) {
+                    last = L.v[a] * Uc.v[b];
+                    s -= last;
+                } else {
+                    last = 0.0;
+                }
+                a += ka <= kb;
+                b += kb <= ka;
+            }
+            s += last;
+            if (r > c) {
+                const double w = s / Uc.v[Uc.rp[c + 1] - 1];
+                if (std::isfinite(w)) L.v[a - 1] = w;
+            } else if (std::isfinite(s)) {
+                Uc.v[b - 1] = s;
+            }
+        }
+    U = transpose(Uc);
+}
+
+// ISAI of a triangular factor, sparsity power 1: row i of M solves (M T)(i, J) = e_i(J) on
+// the pattern J of row i of T, i.e. the dense system T(J, J)^T m = e.
+void isai_tri(HostCsr T, bool lower, HostCsr &M)
+{
+    sort_rows(T);
+    M = T;
+    const int32_t n = T.nrows;
+#pragma omp parallel
+    {
+        std::vector<double> tri, m;
+#pragma omp for schedule(static)
+        for (int32_t row = 0; row < n; ++row) {
+            const int32_t b = T.rp[row], sz = T.rp[row + 1] - b;
+            if (sz == 0) continue;
+            tri.assign((size_t)sz * sz, 0.0);
+            for (int32_t i = 0; i < sz; ++i) {
+                const int32_t r2 = T.ci[b + i];
+                int32_t ka = T.rp[r2], kb = b;
+                while (ka < T.rp[r2 + 1] && kb < T.rp[row + 1]) {
+                    if (T.ci[ka] == T.ci[kb]) {
+                        tri[(size_t)i * sz + (kb - b)] = T.v[ka];
+                        ++ka;
+                        ++kb;
+                    } else if (T.ci[ka] < T.ci[kb]) {
+                        ++ka;
+                    } else {
+                        ++kb;
+                    }
+                }
+            }
+            m.assign(sz, 0.0);
+            if (lower) {
+                m[sz - 1] = 1.0;
+                for (int32_t c = sz - 1; c >= 0; --c) {
+                    const double t = m[c] / tri[(size_t)c * sz + c];
+                    m[c] = t;
+                    for (int32_t r = c - 1; r >= 0; --r) m[r] -= t * tri[(size_t)c * sz + r];
+                }
+            } else {
+                m[0] = 1.0;
+                for (int32_t c = 0; c < sz; ++c) {
+                    const double t = m[c] / tri[(size_t)c * sz + c];
+                    m[c] = t;
+                    for (int32_t r = c + 1; r < sz; ++r) m[r] -= t * tri[(size_t)c * sz + r];
+                }
+            }
+            bool finite = true;
+            for (int32_t i = 0; i < sz; ++i) finite = finite && std::isfinite(m[i]);
+            for (int32_t i = 0; i < sz; ++i)
+                M.v[b + i] = finite ? m[i] : (T.ci[b + i] == row ? 1.0 : 0.0);
+        }
+    }
+}
+
+}  // namespace
+
+// =============================================================================
+// block-Jacobi apply.  A CTA owns a tile of kBlock consecutive rows, one row per thread.
+// r for the tile (plus 31 rows either side: a block has at most 32 rows and may straddle
+// the tile edge) is staged in shared memory; the threads of a block then read the same
+// r[inner] (broadcast) and consecutive entries of the column-major inverse (coalesced,
+// streamed once).  z_i = sum_inner Dinv[i][inner] r[inner], inner ascending from 0.0 -
+// the order of Ginkgo's reference apply.  r.z is reduced per CTA and finished by the last
+// CTA in a fixed order.
+// Algorithmic bytes: sum_blocks 8 bs^2 (inverse) + 8 n (r) + 8 n (z) + 4 n (row -> block).
+// =============================================================================
+constexpr int kBjHalo = 31;
+
+__global__ void __launch_bounds__(kBlock)
+    block_jacobi_apply_kernel(int32_t n, int32_t ntiles, const int32_t *__restrict__ row_block,
+                              const int32_t *__restrict__ block_ptrs,
+                              const int64_t *__restrict__ block_off,
+                              const double *__restrict__ inv, const double *__restrict__ r,
+                              double *__restrict__ z, double *partials, unsigned int *ticket,
+                              double *result, const int32_t *stop)
+{
+    __shared__ double s_r[kBlock + 2 * kBjHalo];
+    __shared__ double s_warp[kBlock / 32];
+    if (stop != nullptr && *stop != 0) return;
+    double red = 0.0;
+    for (int32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int32_t t0 = tile * kBlock;
+        __syncthreads();   // s_r of the previous tile is no longer read
+        for (int32_t k = threadIdx.x; k < kBlock + 2 * kBjHalo; k += kBlock) {
+            const int32_t g = t0 - kBjHalo + k;
+            s_r[k] = (g >= 0 && g < n) ? r[g] : 0.0;
+        }
+        __syncthreads();
+        const int32_t row = t0 + threadIdx.x;
+        if (row < n) {
+            const int32_t b = row_block[row];
+            const int32_t r0 = block_ptrs[b], bs = block_ptrs[b + 1] - r0;
+            const double *col = inv + block_off[b] + (row - r0);
+            const double *rb = s_r + (r0 - t0 + kBjHalo);
+            double acc = 0.0;
+            int32_t inner = 0;
+            for (; inner + 4 <= bs; inner += 4) {
+                const double a0 = __ldcs(col + (size_t)(inner + 0) * bs);
+                const double a1 = __ldcs(col + (size_t)(inner + 1) * bs);
+                const double a2 = __ldcs(col + (size_t)(inner + 2) * bs);
+                const double a3 = __ldcs(col + (size_t)(inner + 3) * bs);
+                acc += a0 * rb[inner + 0];
+                acc += a1 * rb[inner + 1];
+                acc += a2 * rb[inner + 2];
+                acc += a3 * rb[inner + 3];
+            }
+            for (; inner < bs; ++inner) acc += __ldcs(col + (size_t)inner * bs) * rb[inner];
+            z[row] = acc;
+            red += acc * s_r[threadIdx.x + kBjHalo];
+        }
+    }
+    if (result == nullptr) return;
+    red = block_sum(red, s_warp);
+    if (threadIdx.x == 0) partials[blockIdx.x] = red;
+    if (last_cta(ticket)) {
+        const double tot = reduce_partials(partials, gridDim.x, s_warp);
+        if (threadIdx.x == 0) *result = tot;
+    }
+}
+
+// r.z with a stop flag (after the triangular solves of the ILU preconditioner)
+__global__ void __launch_bounds__(kBlock)
+    precond_dot_kernel(int64_t n, const double *__restrict__ a, const double *__restrict__ b,
+                       double *partials, unsigned int *ticket, double *result,
+                       const int32_t *stop)
+{
+    __shared__ double s_warp[kBlock / 32];
+    if (stop != nullptr && *stop != 0) return;
+    double s = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * kBlock)
+        s += a[i] * b[i];
+    s = block_sum(s, s_warp);
+    if (threadIdx.x == 0) partials[blockIdx.x] = s;
+    if (last_cta(ticket)) {
+        const double tot = reduce_partials(partials, gridDim.x, s_warp);
+        if (threadIdx.x == 0) *result = tot;
+    }
+}
+
+// =============================================================================
+// Preconditioner
+// =============================================================================
+void PrecondData::generate(int32_t n, const int32_t *rp, const int32_t *ci, const double *v,
+                           int32_t kind, int32_t max_block_size)
+{
+    SCHWZ_REQUIRE(kind >= PRECOND_BLOCK_JACOBI && kind <= PRECOND_ISAI,
+                  "Unsupported preconditioner.");   // solve.cpp:566, :651
+    *this = PrecondData();
+    if (kind == PRECOND_BLOCK_JACOBI) {
+        SCHWZ_REQUIRE(max_block_size >= 1 && max_block_size <= 32,
+                      "block-Jacobi max_block_size must be in [1, 32]");
+        find_blocks(n, rp, ci, max_block_size, block_ptrs);
+        const size_t nb = block_ptrs.size() - 1;
+        block_off.assign(nb + 1, 0);
+        for (size_t b = 0; b < nb; ++b) {
+            const int64_t bs = block_ptrs[b + 1] - block_ptrs[b];
+            block_off[b + 1] = block_off[b] + bs * bs;
+        }
+        blocks.assign((size_t)block_off[nb], 0.0);
+#pragma omp parallel
+        {
+            double B[32 * 32];
+#pragma omp for schedule(dynamic, 256)
+            for (int64_t b = 0; b < (int64_t)nb; ++b) {
+                const int32_t r0 = block_ptrs[b], bs = block_ptrs[b + 1] - r0;
+                std::fill(B, B + bs * bs, 0.0);
+                for (int32_t i = 0; i < bs; ++i)
+                    for (int32_t k = rp[r0 + i]; k < rp[r0 + i + 1]; ++k)
+                        if (ci[k] >= r0 && ci[k] < r0 + bs) B[i * bs + (ci[k] - r0)] = v[k];
+                invert_block(B, bs, blocks.data() + block_off[b]);
+            }
+        }
+        return;
+    }
+    HostCsr A;
+    A.nrows = A.ncols = n;
+    A.rp.assign(rp, rp + n + 1);
+    A.ci.assign(ci, ci + rp[n]);
+    A.v.assign(v, v + rp[n]);
+    par_ilu(std::move(A), L, U);
+    if (kind == PRECOND_ISAI) {
+        isai_tri(L, true, Li);
+        isai_tri(U, false, Ui);
+    }
+}
+
+Preconditioner::Preconditioner(const Ctx &ctx, int32_t n, const int32_t *rp, const int32_t *ci,
+                               const double *v, int32_t kind, int32_t max_block_size)
+    : ctx_(ctx), n_(n), kind_(kind)
+{
+    host.generate(n, rp, ci, v, kind, max_block_size);
+    ctx.use();
+    if (kind == PRECOND_BLOCK_JACOBI) {
+        std::vector<int32_t> row_block((size_t)n);
+        for (size_t b = 0; b + 1 < host.block_ptrs.size(); ++b)
+            for (int32_t i = host.block_ptrs[b]; i < host.block_ptrs[b + 1]; ++i)
+                row_block[i] = (int32_t)b;
+        inv_bytes_ = 8 * host.block_off.back();
+        dev_block_ptrs_ = ctx.upload(host.block_ptrs.data(), host.block_ptrs.size());
+        dev_block_off_ = ctx.upload(host.block_off.data(), host.block_off.size());
+        dev_row_block_ = ctx.upload(row_block.data(), row_block.size());
+        dev_blocks_ = ctx.upload(host.blocks.data(), host.blocks.size());
+        return;
+    }
+    if (kind == PRECOND_ILU) {
+        Ltrs_.reset(new TrsPlan(ctx, n, host.L.rp.data(), host.L.ci.data(), host.L.v.data(), false));
+        Utrs_.reset(new TrsPlan(ctx, n, host.U.rp.data(), host.U.ci.data(), host.U.v.data(), true));
+    } else {
+        dev_Li_.reset(csr_upload(ctx, n, n, host.Li.rp.data(), host.Li.ci.data(), host.Li.v.data()));
+        dev_Ui_.reset(csr_upload(ctx, n, n, host.Ui.rp.data(), host.Ui.ci.data(), host.Ui.v.data()));
+    }
+    tmp_ = ctx.alloc_zero<double>((size_t)n);
+    if (kind == PRECOND_ILU) in_ = ctx.alloc_zero<double>((size_t)n);
+}
+
+Preconditioner::~Preconditioner()
+{
+    ctx_.release(dev_block_ptrs_);
+    ctx_.release(dev_block_off_);
+    ctx_.release(dev_row_block_);
+    ctx_.release(dev_blocks_);
+    ctx_.release(tmp_);
+    ctx_.release(in_);
+}
+
+void Preconditioner::release_host() { host = PrecondData(); }
+
+int64_t Preconditioner::bytes_per_apply() const
+{
+    switch (kind_) {
+    case PRECOND_BLOCK_JACOBI: return inv_bytes_ + 20 * (int64_t)n_;
+    case PRECOND_ILU: return 12 * (Ltrs_->nnz() + Utrs_->nnz()) + 2 * 20 * (int64_t)n_ + 16 * (int64_t)n_;
+    case PRECOND_ISAI:
+        return 12 * (dev_Li_->nnz + dev_Ui_->nnz) + 2 * (4 * ((int64_t)n_ + 1) + 16 * (int64_t)n_) +
+               8 * (int64_t)n_;
+    }
+    return 0;
+}
+
+void Preconditioner::apply(const double *r, double *z, double *dot_result, const int32_t *stop)
+{
+    ctx_.use();
+    if (n_ == 0) return;
+    switch (kind_) {
+    case PRECOND_BLOCK_JACOBI: {
+        const int32_t ntiles = (n_ + kBlock - 1) / kBlock;
+        const int grid = std::min(ntiles, kVecGrid);
+        block_jacobi_apply_kernel<<<grid, kBlock, 0, ctx_.stream>>>(
+            n_, ntiles, dev_row_block_, dev_block_ptrs_, dev_block_off_, dev_blocks_, r, z,
+            ctx_.partials, ctx_.tickets + 8, dot_result, stop);
+        SCHWZ_CUDA(cudaGetLastError());
+        count_launch();
+        return;
+    }
+    case PRECOND_ILU: {
+        // the level launches are captured per (input, output) pair: stage the input so that
+        // GMRES, which hands in a different basis vector every step, reuses one graph
+        SCHWZ_CUDA(cudaMemcpyAsync(in_, r, sizeof(double) * (size_t)n_, cudaMemcpyDeviceToDevice,
+                                   ctx_.stream));
+        Ltrs_->solve(in_, tmp_, stop);
+        Utrs_->solve(tmp_, z, stop);
+        if (dot_result) {
+            const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((n_ + kBlock - 1) / kBlock, kVecGrid));
+            precond_dot_kernel<<<grid, kBlock, 0, ctx_.stream>>>(n_, r, z, ctx_.partials,
+                                                                 ctx_.tickets + 8, dot_result, stop);
+            SCHWZ_CUDA(cudaGetLastError());
+            count_launch();
+        }
+        return;
+    }
+    case PRECOND_ISAI:
+        launch_spmv(ctx_, *dev_Li_, 1.0, r, 0.0, nullptr, tmp_, EPI_NONE, nullptr, nullptr, 0, stop);
+        if (dot_result)
+            launch_spmv(ctx_, *dev_Ui_, 1.0, tmp_, 0.0, nullptr, z, EPI_DOT, r, dot_result, n_, stop);
+        else
+            launch_spmv(ctx_, *dev_Ui_, 1.0, tmp_, 0.0, nullptr, z, EPI_NONE, nullptr, nullptr, 0, stop);
+        return;
+    }
+}
+
+}  // namespace schwz_b200

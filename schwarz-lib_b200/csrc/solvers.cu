@@ -33,32 +33,48 @@ CgSolver::~CgSolver()
     ctx_.release(r_);
     ctx_.release(p_);
     ctx_.release(q_);
+    ctx_.release(z_);
     ctx_.release(s_);
     if (pinned_stop_) cudaFreeHost(pinned_stop_);
     for (auto &e : ev_)
         if (e) cudaEventDestroy(e);
 }
 
+void CgSolver::set_precond(Preconditioner *M)
+{
+    M_ = M;
+    if (M_ && !z_) z_ = ctx_.alloc_zero<double>(n_);
+}
+
 int64_t CgSolver::bytes_per_iteration() const
 {
     // SpMV (q = A p, p.q fused) + x/r update (4 reads, 2 writes) + p update
     // (2 reads, 1 write): SURVEY.md 8(d) minus the traffic the fusion removes
-    return 12 * A_.nnz + 4 * (n_ + 1) + 16 * n_ + 48 * n_ + 24 * n_;
+    return 12 * A_.nnz + 4 * (n_ + 1) + 16 * n_ + 48 * n_ + 24 * n_ +
+           (M_ ? M_->bytes_per_apply() : 0);
 }
 
 void CgSolver::iteration(double *x)
 {
-    launch_cg_p_update(ctx_, n_, r_, p_, s_);
+    if (M_) {
+        // z = M^-1 r with rho = r.z fused; the x/r update below then leaves rho alone and
+        // only produces ||r|| for the stop test (which Ginkgo evaluates after rho, before
+        // the p update - the order of the two does not change any number)
+        M_->apply(r_, z_, &s_->rho, &s_->stop);
+        launch_cg_p_update(ctx_, n_, z_, p_, s_);
+    } else {
+        launch_cg_p_update(ctx_, n_, r_, p_, s_);
+    }
     launch_spmv(ctx_, A_, 1.0, p_, 0.0, nullptr, q_, EPI_DOT, p_, &s_->beta, (int32_t)n_,
                 &s_->stop);
-    launch_cg_xr_update(ctx_, n_, x, r_, p_, q_, s_);
+    launch_cg_xr_update(ctx_, n_, x, r_, p_, q_, s_, M_ != nullptr);
 }
 
 void CgSolver::solve(const double *b, double *x, int32_t max_iters, double tol,
                      const int32_t *outer_stop)
 {
     SCHWZ_REQUIRE(((uintptr_t)x & 15) == 0, "CG solution vector must be 16-byte aligned");
-    if (g_use_small_solvers && cg_small_fits(n_)) {
+    if (g_use_small_solvers && cg_small_fits(n_) && !M_) {
         // whole solve in one launch (small_solvers.cu)
         launch_cg_small(ctx_, A_, b, x, max_iters, tol, s_, outer_stop);
         return;
@@ -104,7 +120,7 @@ void CgSolver::bench_step(int kind, double *scratch_x)
         SCHWZ_CUDA(cudaStreamSynchronize(ctx_.stream));
         return;
     }
-    if (kind == 1) launch_cg_xr_update(ctx_, n_, scratch_x, r_, p_, q_, s_);
+    if (kind == 1) launch_cg_xr_update(ctx_, n_, scratch_x, r_, p_, q_, s_, false);
     else launch_cg_p_update(ctx_, n_, r_, p_, s_);
 }
 
@@ -291,10 +307,32 @@ GmresSolver::~GmresSolver()
 {
     ctx_.release(V_);
     ctx_.release(w_);
+    ctx_.release(pv_);
+    ctx_.release(upd_);
     ctx_.release(small_);
     if (pinned_stop_) cudaFreeHost(pinned_stop_);
     for (auto &e : ev_)
         if (e) cudaEventDestroy(e);
+}
+
+void GmresSolver::set_precond(Preconditioner *M)
+{
+    M_ = M;
+    if (M_ && !pv_) {
+        pv_ = ctx_.alloc_zero<double>(n_);
+        upd_ = ctx_.alloc_zero<double>(n_);
+    }
+}
+
+// x += pv  (the preconditioned update M^-1 (V y)); same guard as gmres_update_x_kernel
+__global__ void __launch_bounds__(kBlock)
+    gmres_add_kernel(int64_t n, const GmresState *st, const double *__restrict__ pv,
+                     double *__restrict__ x, int only_if_restart)
+{
+    if (only_if_restart && (st->stop || !st->need_restart)) return;
+    for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * kBlock)
+        x[i] += pv[i];
 }
 
 static int vgrid(int64_t n)
@@ -310,7 +348,7 @@ void GmresSolver::solve(const double *b, double *x, int32_t max_iters, double to
     GmresState *S = (GmresState *)(small_ + small);
     double *H = small_;
     const int g = vgrid(n_);
-    if (g_use_small_solvers && gmres_small_fits(n_, m_)) {
+    if (g_use_small_solvers && gmres_small_fits(n_, m_) && !M_) {
         launch_gmres_small(ctx_, A_, b, x, V_, m_, max_iters, tol, &S->resnorm, &S->r0, &S->total);
         return;
     }
@@ -322,6 +360,21 @@ void GmresSolver::solve(const double *b, double *x, int32_t max_iters, double to
         gmres_begin_cycle_kernel<<<1, 1, 0, st>>>(S, small_, first, max_iters, tol, m_);
         gmres_scale_kernel<<<g, kBlock, 0, st>>>(n_, w_, V_, &S->tmp, S, 0);
         count_launch(2);
+    };
+    // x += V y, or x += M^-1 (V y) with a preconditioner (V y accumulated from zero, columns
+    // ascending, as Ginkgo's calculate_qy does)
+    auto update_x = [&](int only_if_restart) {
+        gmres_backsolve_kernel<<<1, 1, 0, st>>>(S, small_, only_if_restart);
+        if (!M_) {
+            gmres_update_x_kernel<<<g, kBlock, 0, st>>>(n_, S, small_, V_, x, only_if_restart);
+            count_launch(2);
+            return;
+        }
+        SCHWZ_CUDA(cudaMemsetAsync(upd_, 0, sizeof(double) * (size_t)n_, st));
+        gmres_update_x_kernel<<<g, kBlock, 0, st>>>(n_, S, small_, V_, upd_, only_if_restart);
+        M_->apply(upd_, pv_, nullptr, nullptr);
+        gmres_add_kernel<<<g, kBlock, 0, st>>>(n_, S, pv_, x, only_if_restart);
+        count_launch(3);
     };
     begin_cycle(1);
     pinned_stop_[0] = pinned_stop_[1] = 0;
@@ -335,9 +388,7 @@ void GmresSolver::solve(const double *b, double *x, int32_t max_iters, double to
         if (total == max_iters) break;   // the test above has set stop
         if (k == m_) {
             // restart: x += V y ; new residual ; new cycle (no-ops when stopped)
-            gmres_backsolve_kernel<<<1, 1, 0, st>>>(S, small_, 1);
-            gmres_update_x_kernel<<<g, kBlock, 0, st>>>(n_, S, small_, V_, x, 1);
-            count_launch(2);
+            update_x(1);
             // the cycle restart must not run once stopped: guard through S->stop
             launch_spmv(ctx_, A_, -1.0, x, 1.0, b, w_, EPI_NRM2, nullptr, &S->tmp, (int32_t)n_,
                         &S->stop);
@@ -347,8 +398,14 @@ void GmresSolver::solve(const double *b, double *x, int32_t max_iters, double to
             k = 0;
         }
         // Arnoldi step k: w = A V_k ; MGS against V_0..V_k
-        launch_spmv(ctx_, A_, 1.0, V_ + (size_t)k * n_, 0.0, nullptr, w_, EPI_NONE, nullptr,
-                    nullptr, 0, &S->stop);
+        if (M_) {
+            M_->apply(V_ + (size_t)k * n_, pv_, nullptr, &S->stop);
+            launch_spmv(ctx_, A_, 1.0, pv_, 0.0, nullptr, w_, EPI_NONE, nullptr, nullptr, 0,
+                        &S->stop);
+        } else {
+            launch_spmv(ctx_, A_, 1.0, V_ + (size_t)k * n_, 0.0, nullptr, w_, EPI_NONE, nullptr,
+                        nullptr, 0, &S->stop);
+        }
         double *col = H + (size_t)k * (m_ + 1);
         for (int i = 0; i <= k; ++i) {
             gmres_dot_kernel<<<g, kBlock, 0, st>>>(n_, w_, V_ + (size_t)i * n_, ctx_.partials,
@@ -378,9 +435,7 @@ void GmresSolver::solve(const double *b, double *x, int32_t max_iters, double to
     // final update with the columns of the last (partial) cycle.  When the
     // device stopped earlier than the host schedule, S->k is the true count
     // and the kernels after the stop were no-ops.
-    gmres_backsolve_kernel<<<1, 1, 0, st>>>(S, small_, 0);
-    gmres_update_x_kernel<<<g, kBlock, 0, st>>>(n_, S, small_, V_, x, 0);
-    count_launch(2);
+    update_x(0);
     SCHWZ_CUDA(cudaGetLastError());
 }
 
@@ -432,8 +487,9 @@ __global__ void __launch_bounds__(kBlock)
                       const int32_t *__restrict__ order, const int32_t *__restrict__ rp,
                       const int32_t *__restrict__ ci, const double *__restrict__ v,
                       const double *__restrict__ inv_diag, const double *__restrict__ b,
-                      double *x)
+                      double *x, const int32_t *stop)
 {
+    if (stop != nullptr && *stop != 0) return;
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * kBlock + threadIdx.x) >> 5;
     const int nwarps = (gridDim.x * kBlock) >> 5;
@@ -458,10 +514,11 @@ __global__ void __launch_bounds__(kBlock)
                      const int32_t *__restrict__ crp, const int32_t *__restrict__ cci,
                      const double *__restrict__ cv, const double *__restrict__ dinv,
                      const double *__restrict__ b, double *x, double *t_scratch,
-                     unsigned int *ticket)
+                     unsigned int *ticket, const int32_t *stop)
 {
     __shared__ double s_t[kTrsBlock];
     __shared__ bool s_last;
+    if (stop != nullptr && *stop != 0) return;
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * kBlock + threadIdx.x) >> 5;
     const int nwarps = (gridDim.x * kBlock) >> 5;
@@ -615,7 +672,7 @@ TrsPlan::TrsPlan(const Ctx &ctx, int32_t n, const int32_t *rp, const int32_t *ci
 
 TrsPlan::~TrsPlan()
 {
-    if (graph_) cudaGraphExecDestroy(graph_);
+    for (const Captured &c : graphs_) cudaGraphExecDestroy(c.exec);
     ctx_.release(rp_);
     ctx_.release(ci_);
     ctx_.release(v_);
@@ -629,45 +686,46 @@ TrsPlan::~TrsPlan()
     ctx_.release(block_t_);
 }
 
-void TrsPlan::solve(const double *b, double *x)
+void TrsPlan::solve(const double *b, double *x, const int32_t *stop)
 {
     ctx_.use();
     if (n_ == 0) return;
-    if (graph_ && b == graph_b_ && x == graph_x_) {
-        SCHWZ_CUDA(cudaGraphLaunch(graph_, ctx_.stream));
-        count_launch();
-        return;
-    }
-    // capture the level launches once per (b, x) pair
-    if (graph_) {
-        cudaGraphExecDestroy(graph_);
-        graph_ = nullptr;
+    for (const Captured &c : graphs_)
+        if (c.b == b && c.x == x && c.stop == stop) {
+            SCHWZ_CUDA(cudaGraphLaunch(c.exec, ctx_.stream));
+            count_launch(num_launches());
+            return;
+        }
+    // capture the level launches once per (b, x, stop) triple; a few triples are kept (a
+    // preconditioner is applied to different vectors by the same solver)
+    if (graphs_.size() >= 4) {
+        cudaGraphExecDestroy(graphs_.front().exec);
+        graphs_.erase(graphs_.begin());
     }
     cudaGraph_t graph = nullptr;
     SCHWZ_CUDA(cudaStreamBeginCapture(ctx_.stream, cudaStreamCaptureModeThreadLocal));
-    int launches = 0;
     for (const Segment &sg : segments_) {
         if (sg.kind == 0) {
             const int32_t l = sg.a;
             const int32_t rows = level_ptr_[l + 1] - level_ptr_[l];
             const int grid = std::min((rows + kTrsWarps - 1) / kTrsWarps, kVecGrid);
             trs_levels_kernel<<<grid, kBlock, 0, ctx_.stream>>>(l, l + 1, level_ptr_dev_, order_,
-                                                                rp_, ci_, v_, inv_diag_, b, x);
+                                                                rp_, ci_, v_, inv_diag_, b, x,
+                                                                stop);
         } else {
             const int grid = std::max(1, (sg.b + kTrsWarps - 1) / kTrsWarps);
             trs_block_kernel<<<grid, kBlock, 0, ctx_.stream>>>(
                 sg.a, sg.b, order_, chain_rp_, chain_ci_, chain_v_, dinv_ + sg.dinv_off, b, x,
-                block_t_, ctx_.tickets + 6);
+                block_t_, ctx_.tickets + 6, stop);
         }
-        ++launches;
     }
     SCHWZ_CUDA(cudaStreamEndCapture(ctx_.stream, &graph));
-    SCHWZ_CUDA(cudaGraphInstantiate(&graph_, graph, 0));
+    Captured c{b, x, stop, nullptr};
+    SCHWZ_CUDA(cudaGraphInstantiate(&c.exec, graph, 0));
     cudaGraphDestroy(graph);
-    graph_b_ = b;
-    graph_x_ = x;
-    SCHWZ_CUDA(cudaGraphLaunch(graph_, ctx_.stream));
-    count_launch(launches);
+    graphs_.push_back(c);
+    SCHWZ_CUDA(cudaGraphLaunch(c.exec, ctx_.stream));
+    count_launch(num_launches());
 }
 
 }  // namespace schwz_b200

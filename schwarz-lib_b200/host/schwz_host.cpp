@@ -255,11 +255,19 @@ void Solve<V, I, M>::setup_local_solver(
         if (metadata.my_rank == 0) {
             SAY(" Local max iters " << l_max_iters << " with restart iter "
                       << settings.restart_iter);
-            if (metadata.local_precond != "null")
+            // the banners of source/solve.cpp:489-651, verbatim
+            const std::string kry = settings.non_symmetric_matrix ? "GMRES" : "CG";
+            const std::string &pc = metadata.local_precond;
+            if (pc == "block-jacobi")
+                SAY(" Local Ginkgo iterative solve(" << kry << ") with Block-Jacobi preconditioning ");
+            else if (pc == "ilu")
+                SAY(" Local Ginkgo iterative solve(" << kry << ") with ParILU preconditioning ");
+            else if (pc == "isai")
+                SAY(" Local Ginkgo iterative solve(" << kry << ") with ISAIpreconditioning ");
+            else if (pc == "null")
+                SAY(" Local Ginkgo iterative solve(" << kry << ") with no preconditioning ");
+            else
                 std::cerr << "Unsupported preconditioner." << std::endl;
-            SAY((settings.non_symmetric_matrix
-                              ? " Local Ginkgo iterative solve(GMRES) with no preconditioning "
-                              : " Local Ginkgo iterative solve(CG) with no preconditioning "));
         }
     } else {
         throw std::runtime_error("local solver not implemented");
@@ -818,6 +826,16 @@ void SolverRAS<V, I, M>::setup_comm_buffers()
             // (restricted_schwarz.cpp:483-492); with M = double the conversion is the identity
             o.use_mixed_precision =
                 (settings.use_mixed_precision && std::is_same<M, float>::value) ? 1 : 0;
+            // metadata.local_precond (solve.cpp:486-652); an unknown name leaves the solve
+            // unpreconditioned after the "Unsupported preconditioner." message, as upstream
+            if (o.local_solver == 2) {
+                const std::string &pc = metadata.local_precond;
+                o.local_precond = pc == "block-jacobi" ? SCHWZ_PRECOND_BLOCK_JACOBI
+                                  : pc == "ilu"        ? SCHWZ_PRECOND_ILU
+                                  : pc == "isai"       ? SCHWZ_PRECOND_ISAI
+                                                       : SCHWZ_PRECOND_NONE;
+                o.precond_max_block_size = (int32_t)metadata.precond_max_block_size;
+            }
             B200_CHECK(schwz_b200_ras_create(D.ctx, D.setup, me, this->rhs_host_.data(), &o, &D.ras));
             if (D.have_factors)
                 B200_CHECK(schwz_b200_ras_set_factors(D.ras, D.L_rowptr.data(), D.L_col.data(),

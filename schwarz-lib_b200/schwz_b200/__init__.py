@@ -25,7 +25,12 @@ class RasOptions(C.Structure):
     _fields_ = [("tolerance", C.c_double), ("local_tol", C.c_double),
                 ("local_max_iters", C.c_int32), ("local_solver", C.c_int32),
                 ("non_symmetric", C.c_int32), ("restart_iter", C.c_int32),
-                ("overlap", C.c_int32), ("use_mixed_precision", C.c_int32)]
+                ("overlap", C.c_int32), ("use_mixed_precision", C.c_int32),
+                ("local_precond", C.c_int32), ("precond_max_block_size", C.c_int32)]
+
+
+# metadata.local_precond of the reference (--local_precond of bench_ras)
+PRECOND = {"null": 0, "block-jacobi": 1, "ilu": 2, "isai": 3}
 
 
 class MailboxLayout(C.Structure):
@@ -72,7 +77,9 @@ def load():
         for name in ("schwz_b200_launch_count", "schwz_b200_spmv_bytes",
                      "schwz_b200_ras_kernel_bytes",
                      "schwz_b200_host_cholesky", "schwz_b200_laplacian2d",
-                     "schwz_b200_laplacian3d"):
+                     "schwz_b200_laplacian3d", "schwz_b200_precond_bytes_per_apply",
+                     "schwz_b200_precond_block_ptrs", "schwz_b200_precond_blocks",
+                     "schwz_b200_precond_csr"):
             getattr(L, name).restype = C.c_int64
         L.schwz_b200_host_free.restype = None
         _lib = L
@@ -426,11 +433,62 @@ class Csr:
         return int(load().schwz_b200_spmv_bytes(self.h, C.c_int(int(beta_nonzero))))
 
 
+class Precond:
+    """Local preconditioner of CG / GMRES (source/solve.cpp:486-652): generated on the host
+    from the host CSR, applied on the device.  kind in PRECOND.  ctx=None: generation only.
+    The getters must be used before the handle is attached to a large Ras (which drops the
+    host copy)."""
+
+    def __init__(self, ctx, rp, ci, v, kind, max_block_size=16):
+        self.n = len(rp) - 1
+        self.kind = kind
+        h = C.c_void_p()
+        _chk(load().schwz_b200_precond_create(ctx.h if ctx is not None else None,
+                                              C.c_int32(self.n), _p(_i32(rp)),
+                                              _p(_i32(ci)), _p(_f64(v)),
+                                              C.c_int32(PRECOND[kind]),
+                                              C.c_int32(max_block_size), C.byref(h)))
+        self.h = h
+
+    def close(self):
+        if self.h:
+            load().schwz_b200_precond_destroy(self.h)
+            self.h = None
+
+    def apply(self, r_dev, z_dev, dot_dev=None):
+        _chk(load().schwz_b200_precond_apply(self.h, r_dev, z_dev, dot_dev))
+
+    def bytes_per_apply(self):
+        return int(load().schwz_b200_precond_bytes_per_apply(self.h))
+
+    def block_ptrs(self):
+        out = np.zeros(load().schwz_b200_precond_block_ptrs(self.h, None), np.int32)
+        load().schwz_b200_precond_block_ptrs(self.h, _p(out))
+        return out
+
+    def blocks(self):
+        out = np.zeros(load().schwz_b200_precond_blocks(self.h, None), np.float64)
+        load().schwz_b200_precond_blocks(self.h, _p(out))
+        return out
+
+    def csr(self, which):
+        """0 L, 1 U of the ILU(0); 2 / 3 sparse approximate inverses of L / U (ISAI)."""
+        nnz = load().schwz_b200_precond_csr(self.h, C.c_int32(which), None, None, None)
+        rp = np.zeros(self.n + 1, np.int32)
+        ci = np.zeros(nnz, np.int32)
+        v = np.zeros(nnz, np.float64)
+        load().schwz_b200_precond_csr(self.h, C.c_int32(which), _p(rp), _p(ci), _p(v))
+        return rp, ci, v
+
+
 class Cg:
-    def __init__(self, ctx, A):
+    def __init__(self, ctx, A, precond=None):
         h = C.c_void_p()
         _chk(load().schwz_b200_cg_create(ctx.h, A.h, C.byref(h)))
         self.h = h
+        self.precond = precond
+        if precond is not None:
+            _chk(load().schwz_b200_cg_set_precond(self.h, precond.h))
 
     def close(self):
         if self.h:
@@ -450,10 +508,13 @@ class Cg:
 
 
 class Gmres:
-    def __init__(self, ctx, A, restart):
+    def __init__(self, ctx, A, restart, precond=None):
         h = C.c_void_p()
         _chk(load().schwz_b200_gmres_create(ctx.h, A.h, C.c_int32(restart), C.byref(h)))
         self.h = h
+        self.precond = precond
+        if precond is not None:
+            _chk(load().schwz_b200_gmres_set_precond(self.h, precond.h))
 
     def close(self):
         if self.h:
@@ -520,12 +581,14 @@ class Ras:
 
     def __init__(self, ctx, setup, rank, rhs=None, tolerance=1e-6, local_tol=1e-12,
                  local_max_iters=-1, local_solver="iterative-ginkgo", non_symmetric=False,
-                 restart_iter=1, use_mixed_precision=False):
+                 restart_iter=1, use_mixed_precision=False, local_precond="null",
+                 precond_max_block_size=16):
         self.ctx = ctx
         self.rank = rank
         o = RasOptions(tolerance, local_tol, local_max_iters,
                        {"iterative-ginkgo": 2, "direct-ginkgo": 1}[local_solver],
-                       int(non_symmetric), restart_iter, setup.overlap, int(use_mixed_precision))
+                       int(non_symmetric), restart_iter, setup.overlap, int(use_mixed_precision),
+                       PRECOND[local_precond], precond_max_block_size)
         h = C.c_void_p()
         rhs_arr = None if rhs is None else _f64(rhs)
         _chk(load().schwz_b200_ras_create(ctx.h, setup.h, C.c_int32(rank), _p(rhs_arr),

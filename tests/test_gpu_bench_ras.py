@@ -113,6 +113,31 @@ def test_onesided_decentralized_3d(tmp_path):
     assert m and float(m.group(1)) < 1e-4
 
 
+@pytest.mark.parametrize("precond,banner", [
+    ("block-jacobi", " Local Ginkgo iterative solve(CG) with Block-Jacobi preconditioning "),
+    ("ilu", " Local Ginkgo iterative solve(CG) with ParILU preconditioning "),
+    ("isai", " Local Ginkgo iterative solve(CG) with ISAIpreconditioning ")])
+def test_local_precond_flag(tmp_path, orc, precond, banner):
+    """--local_precond / --precond_max_block_size (bench_base.hpp:70-72; solve.cpp:572-652):
+    truncated local solves, so the preconditioner decides the outer iteration count."""
+    out = _run(["--executor=cuda", "--explicit_laplacian", "--set_1d_laplacian_size=48",
+                "--enable_global_check", "--num_iters=2000", "--num_subdomains=4",
+                "--local_max_iters=8", "--local_precond=%s" % precond,
+                "--precond_max_block_size=8"], tmp_path)
+    assert banner in out
+    ob = orc.Problem(*orc.laplacian2d(48), 4)
+    ob.configure(max_iters=2000, enable_global_check=True, local_max_iters=8,
+                 local_precond=precond, precond_max_block_size=8)
+    want = ob.run()
+    ob0 = orc.Problem(*orc.laplacian2d(48), 4)
+    ob0.configure(max_iters=2000, enable_global_check=True, local_max_iters=8)
+    assert want < ob0.run()                     # it does precondition
+    got = int(re.search(r" Rank 0 converged in (\d+) iterations", out).group(1))
+    assert abs(got - want) <= 2                 # truncated CG: see DESIGN.md section 5
+    m = re.search(r"relative residual norm of solution ([0-9.eE+-]+)", out)
+    assert m and float(m.group(1)) < 5e-6
+
+
 def test_error_convention(tmp_path):
     p = subprocess.run([BIN, "--executor=omp", "--explicit_laplacian", "--num_subdomains=1"],
                        cwd=tmp_path, capture_output=True, text=True, timeout=60)
