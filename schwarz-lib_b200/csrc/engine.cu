@@ -324,6 +324,10 @@ float Ras::kernel_time_ms(int kind, int reps)
             exchange_push(0);
             exchange_unpack(0, false);
             break;
+        // 5 / 6: the two halves on their own (call both with the same reps so that the epoch
+        // counters of push and unpack end up in step again)
+        case 5: exchange_push(0); break;
+        case 6: exchange_unpack(0, false); break;
         default: SCHWZ_REQUIRE(cg != nullptr, "no CG solver on this subdomain"); cg->bench_step(kind, work);
         }
     };

@@ -239,7 +239,7 @@ public:
     void reset_state();                                      // x, init_guess <- 0; norms unlatched
     // average duration (ms) of one launch of a hot kernel on this subdomain's
     // data, CUDA events on the subdomain's stream: 0 SpMV+dot (CG q = A p),
-    // 1 x/r update, 2 p update, 3 residual SpMV+norm, 4 halo push+unpack
+    // 1 x/r update, 2 p update, 3 residual SpMV+norm, 4 halo push+unpack, 5 push, 6 unpack
     float kernel_time_ms(int kind, int reps);
 
     const Ctx &ctx;

@@ -257,6 +257,20 @@ void isai_tri(HostCsr T, bool lower, HostCsr &M)
 // =============================================================================
 constexpr int kBjHalo = 31;
 
+template <int BS>
+__device__ __forceinline__ double bj_row(const double *__restrict__ col, const double *rb)
+{
+    // volatile asm keeps the BS loads together in program order, ahead of the first use
+    double a[BS];
+#pragma unroll
+    for (int j = 0; j < BS; ++j)
+        asm volatile("ld.global.cs.f64 %0, [%1];" : "=d"(a[j]) : "l"(col + j * BS));
+    double acc = 0.0;
+#pragma unroll
+    for (int j = 0; j < BS; ++j) acc += a[j] * rb[j];
+    return acc;
+}
+
 __global__ void __launch_bounds__(kBlock)
     block_jacobi_apply_kernel(int32_t n, int32_t ntiles, const int32_t *__restrict__ row_block,
                               const int32_t *__restrict__ block_ptrs,
@@ -283,19 +297,26 @@ __global__ void __launch_bounds__(kBlock)
             const int32_t r0 = block_ptrs[b], bs = block_ptrs[b + 1] - r0;
             const double *col = inv + block_off[b] + (row - r0);
             const double *rb = s_r + (r0 - t0 + kBjHalo);
+            // all the loads of a row are issued before the first use (memory-level
+            // parallelism); the sum itself stays sequential in `inner`.  Blocks of 16 and 8
+            // rows (what max_block_size = 16 / 8 gives on a stencil matrix) get unpredicated
+            // straight-line code.
             double acc = 0.0;
-            int32_t inner = 0;
-            for (; inner + 4 <= bs; inner += 4) {
-                const double a0 = __ldcs(col + (size_t)(inner + 0) * bs);
-                const double a1 = __ldcs(col + (size_t)(inner + 1) * bs);
-                const double a2 = __ldcs(col + (size_t)(inner + 2) * bs);
-                const double a3 = __ldcs(col + (size_t)(inner + 3) * bs);
-                acc += a0 * rb[inner + 0];
-                acc += a1 * rb[inner + 1];
-                acc += a2 * rb[inner + 2];
-                acc += a3 * rb[inner + 3];
+            if (bs == 16) {
+                acc = bj_row<16>(col, rb);
+            } else if (bs == 8) {
+                acc = bj_row<8>(col, rb);
+            } else {
+                for (int32_t i0 = 0; i0 < bs; i0 += 8) {
+                    double a[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        a[j] = (i0 + j < bs) ? __ldcs(col + (size_t)(i0 + j) * bs) : 0.0;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        if (i0 + j < bs) acc += a[j] * rb[i0 + j];
+                }
             }
-            for (; inner < bs; ++inner) acc += __ldcs(col + (size_t)inner * bs) * rb[inner];
             z[row] = acc;
             red += acc * s_r[threadIdx.x + kBjHalo];
         }

@@ -2,7 +2,7 @@
 // BASELINE.json: 400..5100 rows per subdomain).  At that size a Krylov
 // iteration is a few microseconds of work, so the multi-kernel solvers in
 // solvers.cu are bound by launch latency (3 launches per CG iteration,
-// 2k+7 per GMRES step).  Here ONE CTA of 1024 threads runs the whole solve:
+// 2k+7 per GMRES step).  Here ONE CTA (128, 256 or 1024 threads, by size) runs the whole solve:
 // vectors live in shared memory (CG) or in L2-resident global memory (the
 // GMRES basis), reductions are fixed-shape CTA reductions, the matrix streams
 // from L1/L2, and the recurrences / stopping rules are exactly those of
@@ -14,23 +14,31 @@
 
 namespace schwz_b200 {
 
-constexpr int kSmallThreads = 1024;
-constexpr int kSmallWarps = kSmallThreads / 32;
+constexpr int kSmallMaxWarps = 32;
+constexpr int kSmallBuf = 2 * kSmallMaxWarps + 2;   // doubles of reduction scratch
 
-__device__ __forceinline__ double cta_sum(double v, double *buf /* kSmallWarps + 1 */)
+// CTA-wide sum with ONE barrier: the warps leave their partial sums in one of two scratch rows
+// (alternating, so that a row is never overwritten while a slow warp still reads it) and every
+// warp then adds the partials up itself with the same fixed shuffle tree.  These solves are a
+// chain of dependent reductions (k + 2 per GMRES step), so the barrier count is the run time.
+template <int THREADS>
+__device__ __forceinline__ double cta_sum(double v, double *buf, int &phase)
 {
+    constexpr int NW = THREADS / 32;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     v = warp_sum(v);
-    __syncthreads();   // buf may still be read from the previous reduction
-    if (lane == 0) buf[w] = v;
+    double *row = buf + phase * kSmallMaxWarps;
+    phase ^= 1;
+    if (lane == 0) row[w] = v;
     __syncthreads();
-    if (w == 0) {
-        double s = lane < kSmallWarps ? buf[lane] : 0.0;
-        s = warp_sum(s);
-        if (lane == 0) buf[kSmallWarps] = s;
+    if (NW <= 8) {   // a short chain of adds beats a second shuffle tree
+        double s = row[0];
+#pragma unroll
+        for (int i = 1; i < NW; ++i) s += row[i];
+        return s;
     }
-    __syncthreads();
-    return buf[kSmallWarps];
+    double s = lane < NW ? row[lane] : 0.0;
+    return warp_sum(s);
 }
 
 __device__ __forceinline__ double row_dot(const int32_t *__restrict__ rp,
@@ -45,6 +53,7 @@ __device__ __forceinline__ double row_dot(const int32_t *__restrict__ rp,
 // -----------------------------------------------------------------------------
 // CG: x, r, p, q in shared memory.
 // -----------------------------------------------------------------------------
+template <int kSmallThreads>
 __global__ void __launch_bounds__(kSmallThreads, 1)
     cg_small_kernel(int32_t n, const int32_t *__restrict__ rp, const int32_t *__restrict__ ci,
                     const double *__restrict__ v, const double *__restrict__ b, double *x,
@@ -53,6 +62,7 @@ __global__ void __launch_bounds__(kSmallThreads, 1)
     extern __shared__ __align__(16) double sm[];
     double *xs = sm, *r = sm + n, *p = sm + 2 * (size_t)n, *q = sm + 3 * (size_t)n;
     double *buf = sm + 4 * (size_t)n;
+    int phase = 0;
     if (outer_stop != nullptr && *outer_stop != 0) return;
     const int t = threadIdx.x;
     for (int32_t i = t; i < n; i += kSmallThreads) {
@@ -68,7 +78,7 @@ __global__ void __launch_bounds__(kSmallThreads, 1)
         r[i] = acc;
         part += acc * acc;
     }
-    double rho = cta_sum(part, buf);
+    double rho = cta_sum<kSmallThreads>(part, buf, phase);
     const double r0 = sqrt(rho);
     double prev_rho = 1.0, resnorm = r0;
     int iter = 0;
@@ -84,7 +94,7 @@ __global__ void __launch_bounds__(kSmallThreads, 1)
             q[i] = qi;
             part += qi * p[i];
         }
-        const double beta = cta_sum(part, buf);
+        const double beta = cta_sum<kSmallThreads>(part, buf, phase);
         part = 0.0;
         if (beta != 0.0) {
             const double a = rho / beta;
@@ -97,7 +107,7 @@ __global__ void __launch_bounds__(kSmallThreads, 1)
         } else {
             for (int32_t i = t; i < n; i += kSmallThreads) part += r[i] * r[i];
         }
-        const double rho_new = cta_sum(part, buf);
+        const double rho_new = cta_sum<kSmallThreads>(part, buf, phase);
         prev_rho = rho;
         rho = rho_new;
         ++iter;
@@ -117,43 +127,53 @@ __global__ void __launch_bounds__(kSmallThreads, 1)
     }
 }
 
-bool cg_small_fits(int64_t n) { return n > 0 && (4 * n + kSmallWarps + 8) * 8 <= 220 * 1024; }
+bool cg_small_fits(int64_t n) { return n > 0 && (4 * n + kSmallBuf) * 8 <= 220 * 1024; }
+
+// threads by size: few warps make the barriers cheap, many warps hide the row gathers
+static int small_threads(int64_t n) { return n <= 1024 ? 128 : n <= 4096 ? 256 : 1024; }
 
 void launch_cg_small(const Ctx &ctx, const DeviceCsr &A, const double *b, double *x,
                      int32_t max_iters, double tol, CgScalars *out, const int32_t *outer_stop)
 {
     ctx.use();
-    const size_t smem = (4 * (size_t)A.nrows + kSmallWarps + 8) * sizeof(double);
+    const size_t smem = (4 * (size_t)A.nrows + kSmallBuf) * sizeof(double);
     static bool configured[64] = {};
     if (!configured[ctx.device]) {
-        SCHWZ_CUDA(cudaFuncSetAttribute(cg_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        220 * 1024));
+        for (auto *k : {cg_small_kernel<128>, cg_small_kernel<256>, cg_small_kernel<1024>})
+            SCHWZ_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            220 * 1024));
         configured[ctx.device] = true;
     }
-    cg_small_kernel<<<1, kSmallThreads, smem, ctx.stream>>>(A.nrows, A.rp, A.ci, A.v, b, x, max_iters,
-                                                            tol, out, outer_stop);
+    const int th = small_threads(A.nrows);
+    auto *k = th == 128 ? cg_small_kernel<128> : th == 256 ? cg_small_kernel<256>
+                                                           : cg_small_kernel<1024>;
+    k<<<1, th, smem, ctx.stream>>>(A.nrows, A.rp, A.ci, A.v, b, x, max_iters, tol, out, outer_stop);
     SCHWZ_CUDA(cudaGetLastError());
     count_launch();
 }
 
 // -----------------------------------------------------------------------------
-// GMRES(m): w and the small Hessenberg system in shared memory, the Krylov
-// basis V ((m+1) x n) in global memory (L2 resident at these sizes).
+// GMRES(m): w and the small Hessenberg system in shared memory; the Krylov basis V
+// ((m+1) x n) too when it fits (cfg3: 31 x 460 doubles = 114 KB), else in global memory
+// (L2 resident at these sizes).
 // -----------------------------------------------------------------------------
+template <int kSmallThreads>
 __global__ void __launch_bounds__(kSmallThreads, 1)
     gmres_small_kernel(int32_t n, const int32_t *__restrict__ rp, const int32_t *__restrict__ ci,
                        const double *__restrict__ v, const double *__restrict__ b, double *x,
                        double *V, int32_t m, int32_t max_iters, double tol, double *resnorm_out,
-                       double *r0_out, int32_t *total_out)
+                       double *r0_out, int32_t *total_out, int basis_in_smem)
 {
     extern __shared__ __align__(16) double sm[];
+    int phase = 0;
     double *w = sm;                               // n
     double *H = w + n;                            // (m+1)*m, column-major
     double *cs = H + (size_t)(m + 1) * m;         // m
     double *sn = cs + m;                          // m
     double *g = sn + m;                           // m+1
     double *y = g + m + 1;                        // m
-    double *buf = y + m;                          // kSmallWarps+1
+    double *buf = y + m;                          // kSmallBuf
+    if (basis_in_smem) V = buf + kSmallBuf;       // (m+1)*n
     const int t = threadIdx.x;
 
     // r = b - A x ; ||r|| ; V0 = r / ||r||   (x read from global: it changes at restarts)
@@ -166,7 +186,7 @@ __global__ void __launch_bounds__(kSmallThreads, 1)
             w[i] = acc;
             part += acc * acc;
         }
-        const double rn = sqrt(cta_sum(part, buf));
+        const double rn = sqrt(cta_sum<kSmallThreads>(part, buf, phase));
         for (int32_t i = t; i < n; i += kSmallThreads) V[i] = rn != 0.0 ? w[i] / rn : 0.0;
         if (t == 0) {
             for (int i = 0; i <= m; ++i) g[i] = 0.0;
@@ -218,13 +238,13 @@ __global__ void __launch_bounds__(kSmallThreads, 1)
             const double *vi = V + (size_t)i * n;
             double part = 0.0;
             for (int32_t j = t; j < n; j += kSmallThreads) part += w[j] * vi[j];
-            const double h = cta_sum(part, buf);
+            const double h = cta_sum<kSmallThreads>(part, buf, phase);
             if (t == 0) col[i] = h;
             for (int32_t j = t; j < n; j += kSmallThreads) w[j] += (-h) * vi[j];
         }
         double part = 0.0;
         for (int32_t j = t; j < n; j += kSmallThreads) part += w[j] * w[j];
-        const double hn = sqrt(cta_sum(part, buf));
+        const double hn = sqrt(cta_sum<kSmallThreads>(part, buf, phase));
         double *vn = V + (size_t)(k + 1) * n;
         for (int32_t j = t; j < n; j += kSmallThreads) vn[j] = hn != 0.0 ? w[j] / hn : 0.0;
         if (t == 0) {
@@ -248,10 +268,10 @@ __global__ void __launch_bounds__(kSmallThreads, 1)
             col[k + 1] = 0.0;
             g[k + 1] = -sn[k] * g[k];
             g[k] = cs[k] * g[k];
-            buf[kSmallWarps + 1] = fabs(g[k + 1]);
+            buf[kSmallBuf - 1] = fabs(g[k + 1]);
         }
         __syncthreads();   // also makes V_{k+1} (global) visible to the whole CTA
-        resnorm = buf[kSmallWarps + 1];
+        resnorm = buf[kSmallBuf - 1];
         ++k;
     }
     update_x(k);
@@ -262,12 +282,16 @@ __global__ void __launch_bounds__(kSmallThreads, 1)
     }
 }
 
-static size_t gmres_small_smem(int64_t n, int m)
+static size_t gmres_small_smem(int64_t n, int m, bool basis)
 {
-    return ((size_t)n + (size_t)(m + 1) * m + 4 * (size_t)m + 1 + kSmallWarps + 8) * sizeof(double);
+    return ((size_t)n + (size_t)(m + 1) * m + 4 * (size_t)m + 1 + kSmallBuf + 8 +
+            (basis ? (size_t)(m + 1) * n : 0)) * sizeof(double);
 }
 
-bool gmres_small_fits(int64_t n, int m) { return n > 0 && n <= 16384 && gmres_small_smem(n, m) <= 220 * 1024; }
+bool gmres_small_fits(int64_t n, int m)
+{
+    return n > 0 && n <= 16384 && gmres_small_smem(n, m, false) <= 220 * 1024;
+}
 
 void launch_gmres_small(const Ctx &ctx, const DeviceCsr &A, const double *b, double *x, double *V,
                         int32_t m, int32_t max_iters, double tol, double *resnorm_out,
@@ -276,12 +300,18 @@ void launch_gmres_small(const Ctx &ctx, const DeviceCsr &A, const double *b, dou
     ctx.use();
     static bool configured[64] = {};
     if (!configured[ctx.device]) {
-        SCHWZ_CUDA(cudaFuncSetAttribute(gmres_small_kernel,
-                                        cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        for (auto *k : {gmres_small_kernel<128>, gmres_small_kernel<256>, gmres_small_kernel<1024>})
+            SCHWZ_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            220 * 1024));
         configured[ctx.device] = true;
     }
-    gmres_small_kernel<<<1, kSmallThreads, gmres_small_smem(A.nrows, m), ctx.stream>>>(
-        A.nrows, A.rp, A.ci, A.v, b, x, V, m, max_iters, tol, resnorm_out, r0_out, total_out);
+    const bool basis = gmres_small_smem(A.nrows, m, true) <= 220 * 1024;
+    const int th = small_threads(A.nrows);
+    auto *k = th == 128 ? gmres_small_kernel<128> : th == 256 ? gmres_small_kernel<256>
+                                                              : gmres_small_kernel<1024>;
+    k<<<1, th, gmres_small_smem(A.nrows, m, basis), ctx.stream>>>(
+        A.nrows, A.rp, A.ci, A.v, b, x, V, m, max_iters, tol, resnorm_out, r0_out, total_out,
+        basis ? 1 : 0);
     SCHWZ_CUDA(cudaGetLastError());
     count_launch();
 }
