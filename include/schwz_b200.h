@@ -171,9 +171,26 @@ int64_t schwz_b200_host_cholesky(int32_t n, const int32_t *rowptr,
                                  const int32_t *col, const double *val,
                                  const int32_t *perm, int32_t *L_rowptr,
                                  int32_t *L_col, double *L_val);
-/* host: fill-reducing ordering (METIS_NodeND of the toolkit's static METIS) */
+/* host: fill-reducing ordering (METIS_NodeND of the toolkit's static METIS) of the pattern
+ * of A + A^T */
 int schwz_b200_host_nd_ordering(int32_t n, const int32_t *rowptr,
                                 const int32_t *col, int32_t *perm);
+
+/* host: sparse LU with threshold partial pivoting, P A Q = L U, L unit lower / U upper CSR with
+ * sorted rows; replaces umfpack_di_symbolic / _numeric / _get_numeric of the UMFPACK branch
+ * (source/solve.cpp:145-171, 322-385; --local_factorization=umfpack).  col_perm = Q (NULL =
+ * natural), the row order P is found (row_perm[k] = row of A that became pivot row k); the
+ * diagonal entry is preferred as pivot while |a_diag| >= diag_pivot_tol * max|column| (UMFPACK's
+ * symmetric strategy uses 1e-3).  No row scaling (the reference fetches UMFPACK's and never
+ * applies it). */
+typedef struct schwz_lu schwz_lu;
+int schwz_b200_host_lu_create(int32_t n, const int32_t *rowptr, const int32_t *col,
+                              const double *val, const int32_t *col_perm, double diag_pivot_tol,
+                              schwz_lu **out);
+int schwz_b200_host_lu_destroy(schwz_lu *lu);
+int schwz_b200_host_lu_nnz(const schwz_lu *lu, int64_t *nnz_l, int64_t *nnz_u);
+int schwz_b200_host_lu_get(const schwz_lu *lu, int32_t *L_rowptr, int32_t *L_col, double *L_val,
+                           int32_t *U_rowptr, int32_t *U_col, double *U_val, int32_t *row_perm);
 
 /* ---- host index sets ---------------------------------------------------------
  * replaces: Initialize::setup_global_matrix / partition
@@ -251,6 +268,10 @@ int schwz_b200_ras_destroy(schwz_ras *r);
 int schwz_b200_ras_set_factors(schwz_ras *r, const int32_t *L_rowptr,
                                const int32_t *L_col, const double *L_val,
                                const int32_t *perm);
+/* direct variant, unsymmetric: the factors of schwz_b200_host_lu_create and the column order it
+ * was given; local solve = Q U^-1 L^-1 P b (local_perm = P, local_inv_perm = Q of
+ * source/solve.cpp:342-353) */
+int schwz_b200_ras_set_lu_factors(schwz_ras *r, const schwz_lu *lu, const int32_t *col_perm);
 /* mailbox = peer-visible block holding the two receive buffers (epoch
  * parity), the epoch flags and the convergence flags of a subdomain; this is
  * what replaces the MPI windows.  The layout travels with the base pointer. */

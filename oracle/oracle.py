@@ -47,6 +47,7 @@ class OrcOptions(C.Structure):
         ("use_mixed_precision", C.c_int32),
         ("local_precond", C.c_int32),
         ("precond_max_block_size", C.c_int32),
+        ("local_factorization", C.c_int32),
     ]
 
 
@@ -343,7 +344,7 @@ class Problem:
                   global_convergence_type="centralized-tree",
                   enable_accumulate=False, iter_offset=False, factor_perms=None,
                   use_mixed_precision=False, local_precond="null",
-                  precond_max_block_size=16):
+                  precond_max_block_size=16, local_factorization="cholmod"):
         o = OrcOptions()
         o.tolerance = tolerance
         o.local_tol = local_tol
@@ -363,6 +364,7 @@ class Problem:
         o.use_mixed_precision = int(use_mixed_precision)
         o.local_precond = PRECOND[local_precond]
         o.precond_max_block_size = precond_max_block_size
+        o.local_factorization = {"cholmod": 0, "umfpack": 1}[local_factorization]
         perm_all = None
         if factor_perms is not None:
             perm_all = np.ascontiguousarray(np.concatenate(factor_perms), np.int32)

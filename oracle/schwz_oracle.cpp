@@ -227,6 +227,7 @@ struct Options {
     int use_mixed_precision = 0;    // settings.use_mixed_precision with MixedValueType = float
     int local_precond = 0;          // metadata.local_precond: 0 null, 1 block-jacobi, 2 ilu, 3 isai
     int precond_max_block_size = 16;  // metadata.precond_max_block_size
+    int local_factorization = 0;    // settings.factorization: 0 "cholmod" (LL^T), 1 "umfpack" (LU)
 };
 
 struct Precond;
@@ -253,7 +254,7 @@ struct Rank {
     std::vector<int> local_iter_hist; // inner iterations per outer iteration
     // direct solver
     Csr L, U;
-    std::vector<idx> fperm;
+    std::vector<idx> fperm, fperm_col;   // local_perm (P) and local_inv_perm (Q; empty = P)
     int last_local_iters = 0;
 };
 
@@ -1112,6 +1113,62 @@ bool cholesky(const Csr &A, const std::vector<idx> &perm, Csr &L)
     return true;
 }
 
+// UMFPACK branch of the factorised variant (source/solve.cpp:145-171, 322-385): the reference
+// takes P, Q, L, U with P A Q = L U from UMFPACK (its row scaling is fetched but never applied,
+// SURVEY Appendix D) and solves x = Q U^-1 L^-1 P b with Ginkgo's triangular solvers.  UMFPACK
+// is not available; the oracle does its own dense LU with partial pivoting (Q = identity, P
+// from the pivot search, first row of largest magnitude) and keeps the factors as CSR.  Small
+// cases only (O(n^3)).
+bool dense_lu(const Csr &A, Csr &L, Csr &U, std::vector<idx> &p)
+{
+    const idx n = A.nrows;
+    std::vector<double> M((size_t)n * n, 0.0);
+    for (idx i = 0; i < n; ++i)
+        for (idx k = A.rp[i]; k < A.rp[i + 1]; ++k) M[(size_t)i * n + A.ci[k]] += A.v[k];
+    p.resize(n);
+    std::iota(p.begin(), p.end(), 0);
+    for (idx k = 0; k < n; ++k) {
+        idx piv = k;
+        for (idx i = k + 1; i < n; ++i)
+            if (std::fabs(M[(size_t)i * n + k]) > std::fabs(M[(size_t)piv * n + k])) piv = i;
+        if (M[(size_t)piv * n + k] == 0.0) return false;
+        if (piv != k) {
+            for (idx j = 0; j < n; ++j) std::swap(M[(size_t)k * n + j], M[(size_t)piv * n + j]);
+            std::swap(p[k], p[piv]);
+        }
+        const double d = M[(size_t)k * n + k];
+#pragma omp parallel for num_threads(g_threads) schedule(static)
+        for (idx i = k + 1; i < n; ++i) {
+            double &lik = M[(size_t)i * n + k];
+            if (lik == 0.0) continue;
+            lik /= d;
+            for (idx j = k + 1; j < n; ++j) M[(size_t)i * n + j] -= lik * M[(size_t)k * n + j];
+        }
+    }
+    L = Csr();
+    U = Csr();
+    L.nrows = L.ncols = U.nrows = U.ncols = n;
+    L.rp.assign(n + 1, 0);
+    U.rp.assign(n + 1, 0);
+    for (idx i = 0; i < n; ++i) {
+        for (idx j = 0; j < i; ++j)
+            if (M[(size_t)i * n + j] != 0.0) {
+                L.ci.push_back(j);
+                L.v.push_back(M[(size_t)i * n + j]);
+            }
+        L.ci.push_back(i);
+        L.v.push_back(1.0);
+        for (idx j = i; j < n; ++j)
+            if (j == i || M[(size_t)i * n + j] != 0.0) {
+                U.ci.push_back(j);
+                U.v.push_back(M[(size_t)i * n + j]);
+            }
+        L.rp[i + 1] = (idx)L.ci.size();
+        U.rp[i + 1] = (idx)U.ci.size();
+    }
+    return true;
+}
+
 Csr transpose(const Csr &A)
 {
     Csr T;
@@ -1465,7 +1522,8 @@ void local_solve(Problem &pb, int me)
         for (idx i = 0; i < n; ++i) perm_sol[i] = R.local_sol[R.fperm[i]];
         lower_trs(R.L, perm_sol, tmp);
         upper_trs(R.U, tmp, perm_sol);
-        for (idx i = 0; i < n; ++i) R.local_sol[R.fperm[i]] = perm_sol[i];
+        const std::vector<idx> &q = R.fperm_col.empty() ? R.fperm : R.fperm_col;
+        for (idx i = 0; i < n; ++i) R.local_sol[q[i]] = perm_sol[i];
         R.local_iter_hist.push_back(0);
     }
 }
@@ -1855,7 +1913,8 @@ struct orc_options {
     int32_t max_iters, local_max_iters, non_symmetric, restart_iter,
         local_solver, enable_onesided, enable_put, enable_one_by_one,
         enable_global_check, conv_tree, conv_decentralized, enable_accumulate,
-        iter_offset, use_mixed_precision, local_precond, precond_max_block_size;
+        iter_offset, use_mixed_precision, local_precond, precond_max_block_size,
+        local_factorization;
 };
 
 void orc_set_rhs(void *h, const double *rhs)
@@ -1889,6 +1948,7 @@ int orc_configure(void *h, const orc_options *o, const idx *perm_all)
     d.use_mixed_precision = o->use_mixed_precision;
     d.local_precond = o->local_precond;
     d.precond_max_block_size = o->precond_max_block_size;
+    d.local_factorization = o->local_factorization;
     d.overlap = pb->overlap;
     setup_windows(*pb);
     setup_vectors(*pb);
@@ -1903,6 +1963,13 @@ int orc_configure(void *h, const orc_options *o, const idx *perm_all)
             else
                 std::iota(R.fperm.begin(), R.fperm.end(), 0);
             off += R.local_size_x;
+            R.fperm_col.clear();
+            if (d.local_factorization == 1) {
+                if (!dense_lu(R.local, R.L, R.U, R.fperm)) return -1;
+                R.fperm_col.resize(R.local_size_x);
+                std::iota(R.fperm_col.begin(), R.fperm_col.end(), 0);
+                continue;
+            }
             if (!cholesky(R.local, R.fperm, R.L)) return -1;
             R.U = transpose(R.L);
         }

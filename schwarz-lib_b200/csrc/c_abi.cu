@@ -448,7 +448,52 @@ int64_t schwz_b200_host_cholesky(int32_t n, const int32_t *rp, const int32_t *ci
 int schwz_b200_host_nd_ordering(int32_t n, const int32_t *rp, const int32_t *ci, int32_t *perm)
 {
     ABI_BEGIN
-    SCHWZ_REQUIRE(nd_ordering(n, rp, ci, perm) == 0, "METIS_NodeND failed");
+    SCHWZ_REQUIRE(nd_ordering_symmetrized(n, rp, ci, perm) == 0, "METIS_NodeND failed");
+    ABI_END
+}
+struct schwz_lu {
+    HostCsr L, U;
+    std::vector<int32_t> p;
+};
+int schwz_b200_host_lu_create(int32_t n, const int32_t *rp, const int32_t *ci, const double *v,
+                              const int32_t *col_perm, double diag_pivot_tol, schwz_lu **out)
+{
+    ABI_BEGIN
+    HostCsr A;
+    A.nrows = A.ncols = n;
+    A.rp.assign(rp, rp + n + 1);
+    A.ci.assign(ci, ci + rp[n]);
+    A.v.assign(v, v + rp[n]);
+    std::unique_ptr<schwz_lu> h(new schwz_lu());
+    SCHWZ_REQUIRE(host_sparse_lu(A, col_perm, diag_pivot_tol, h->L, h->U, h->p),
+                  "matrix is singular");
+    *out = h.release();
+    ABI_END
+}
+int schwz_b200_host_lu_destroy(schwz_lu *lu)
+{
+    ABI_BEGIN
+    delete lu;
+    ABI_END
+}
+int schwz_b200_host_lu_nnz(const schwz_lu *lu, int64_t *nnz_l, int64_t *nnz_u)
+{
+    ABI_BEGIN
+    *nnz_l = lu->L.nnz();
+    *nnz_u = lu->U.nnz();
+    ABI_END
+}
+int schwz_b200_host_lu_get(const schwz_lu *lu, int32_t *Lrp, int32_t *Lci, double *Lv,
+                           int32_t *Urp, int32_t *Uci, double *Uv, int32_t *row_perm)
+{
+    ABI_BEGIN
+    std::copy(lu->L.rp.begin(), lu->L.rp.end(), Lrp);
+    std::copy(lu->L.ci.begin(), lu->L.ci.end(), Lci);
+    std::copy(lu->L.v.begin(), lu->L.v.end(), Lv);
+    std::copy(lu->U.rp.begin(), lu->U.rp.end(), Urp);
+    std::copy(lu->U.ci.begin(), lu->U.ci.end(), Uci);
+    std::copy(lu->U.v.begin(), lu->U.v.end(), Uv);
+    std::copy(lu->p.begin(), lu->p.end(), row_perm);
     ABI_END
 }
 
@@ -659,6 +704,13 @@ int schwz_b200_ras_set_factors(schwz_ras *r, const int32_t *Lrp, const int32_t *
 {
     ABI_BEGIN
     r->impl->set_factors(Lrp, Lci, Lv, perm);
+    ABI_END
+}
+int schwz_b200_ras_set_lu_factors(schwz_ras *r, const schwz_lu *lu, const int32_t *col_perm)
+{
+    ABI_BEGIN
+    r->impl->set_lu_factors(lu->L.rp.data(), lu->L.ci.data(), lu->L.v.data(), lu->U.rp.data(),
+                            lu->U.ci.data(), lu->U.v.data(), lu->p.data(), col_perm);
     ABI_END
 }
 int schwz_b200_ras_mailbox(schwz_ras *r, void **base, schwz_mailbox_layout *l)

@@ -254,7 +254,8 @@ Ras::~Ras()
                     (void *)work, (void *)resnorm_dev, (void *)num_converged_dev,
                     (void *)conv_sent, (void *)mailbox, (void *)in_dst_, (void *)out_src_,
                     (void *)out_off_, (void *)out_dst_dev_[0], (void *)out_dst_dev_[1],
-                    (void *)out_flag_dev_, (void *)out_conv_dev_, (void *)fperm})
+                    (void *)out_flag_dev_, (void *)out_conv_dev_, (void *)fperm,
+                    (void *)fperm_col})
         ctx.release(p);
     if (ev_pushed) cudaEventDestroy(ev_pushed);
     if (pinned_rhs_) cudaFreeHost(pinned_rhs_);
@@ -357,7 +358,28 @@ void Ras::set_factors(const int32_t *Lrp, const int32_t *Lci, const double *Lv,
     std::vector<int32_t> pv(local_size_x);
     for (int32_t i = 0; i < local_size_x; ++i) pv[i] = perm ? perm[i] : i;
     ctx.release(fperm);
+    ctx.release(fperm_col);
+    fperm_col = nullptr;
     fperm = ctx.upload(pv.data(), pv.size());
+}
+
+// LU variant (UMFPACK branch of the reference, source/solve.cpp:322-385): P A Q = L U with
+// local_perm = P (row_permute) and local_inv_perm = Q (inverse row_permute)
+void Ras::set_lu_factors(const int32_t *Lrp, const int32_t *Lci, const double *Lv,
+                         const int32_t *Urp, const int32_t *Uci, const double *Uv,
+                         const int32_t *row_perm, const int32_t *col_perm)
+{
+    Ltrs.reset(new TrsPlan(ctx, local_size_x, Lrp, Lci, Lv, false));
+    Utrs.reset(new TrsPlan(ctx, local_size_x, Urp, Uci, Uv, true));
+    std::vector<int32_t> pv(local_size_x), qv(local_size_x);
+    for (int32_t i = 0; i < local_size_x; ++i) {
+        pv[i] = row_perm ? row_perm[i] : i;
+        qv[i] = col_perm ? col_perm[i] : i;
+    }
+    ctx.release(fperm);
+    ctx.release(fperm_col);
+    fperm = ctx.upload(pv.data(), pv.size());
+    fperm_col = ctx.upload(qv.data(), qv.size());
 }
 
 void Ras::connect(int32_t j, void *peer_base, const MailboxLayout &pl, int32_t peer_recv_offset,
@@ -545,7 +567,7 @@ void Ras::local_solve()
         launch_permute(ctx, local_size_x, fperm, 0, local_sol, perm_sol);
         Ltrs->solve(perm_sol, tmp);
         Utrs->solve(tmp, perm_sol);
-        launch_permute(ctx, local_size_x, fperm, 1, perm_sol, local_sol);
+        launch_permute(ctx, local_size_x, fperm_col ? fperm_col : fperm, 1, perm_sol, local_sol);
     }
 }
 

@@ -212,6 +212,9 @@ public:
 
     void set_factors(const int32_t *Lrp, const int32_t *Lci, const double *Lv,
                      const int32_t *perm);
+    void set_lu_factors(const int32_t *Lrp, const int32_t *Lci, const double *Lv,
+                        const int32_t *Urp, const int32_t *Uci, const double *Uv,
+                        const int32_t *row_perm, const int32_t *col_perm);
     void connect(int32_t j_out, void *peer_base, const MailboxLayout &peer_layout,
                  int32_t peer_recv_offset, int32_t peer_flag_slot, bool same_process);
     // in-neighbour j_in (Get variants): its mailbox and the offset of my block inside its
@@ -258,7 +261,7 @@ public:
     std::unique_ptr<CgSolver> cg;
     std::unique_ptr<GmresSolver> gmres;
     std::unique_ptr<TrsPlan> Ltrs, Utrs;
-    int32_t *fperm = nullptr;
+    int32_t *fperm = nullptr, *fperm_col = nullptr;   // row order P; column order Q (LU only)
     cudaEvent_t ev_pushed = nullptr;
     int32_t last_push_iter = -1;
     int64_t local_nnz = 0;

@@ -301,6 +301,26 @@ int nd_ordering(int32_t n, const int32_t *rp, const int32_t *ci, int32_t *perm)
     return 0;
 }
 
+int nd_ordering_symmetrized(int32_t n, const int32_t *rp, const int32_t *ci, int32_t *perm)
+{
+    // pattern of A + A^T without the diagonal, rows sorted and duplicate-free
+    std::vector<std::vector<int32_t>> adj((size_t)n);
+    for (int32_t i = 0; i < n; ++i)
+        for (int32_t k = rp[i]; k < rp[i + 1]; ++k)
+            if (ci[k] != i) {
+                adj[i].push_back(ci[k]);
+                adj[ci[k]].push_back(i);
+            }
+    std::vector<int32_t> srp((size_t)n + 1, 0), sci;
+    for (int32_t i = 0; i < n; ++i) {
+        std::sort(adj[i].begin(), adj[i].end());
+        adj[i].erase(std::unique(adj[i].begin(), adj[i].end()), adj[i].end());
+        sci.insert(sci.end(), adj[i].begin(), adj[i].end());
+        srp[i + 1] = (int32_t)sci.size();
+    }
+    return nd_ordering(n, srp.data(), sci.data(), perm);
+}
+
 HostCsr transpose(const HostCsr &A)
 {
     HostCsr T;
@@ -320,6 +340,118 @@ HostCsr transpose(const HostCsr &A)
             T.v[q] = A.v[k];
         }
     return T;
+}
+
+// Left-looking sparse LU with threshold partial pivoting, P A Q = L U (replaces
+// umfpack_di_symbolic / umfpack_di_numeric + umfpack_di_get_numeric, source/solve.cpp:145-171,
+// 322-385; the reference never applies UMFPACK's row scaling, SURVEY Appendix D, so none is
+// computed).  Q is given (q[j] = column of A eliminated j-th; a fill-reducing ordering of the
+// pattern of A + A^T), P is found: column j is the sparse triangular solve x = L^-1 A(:, q[j])
+// over the reach of its pattern in the graph of L; the pivot is the diagonal entry A-row q[j]
+// when it is still free and |x| >= diag_tol * max (UMFPACK's "symmetric strategy" preference
+// for the diagonal), else the entry of largest magnitude.  L has a unit diagonal.
+// Returns false for a structurally or numerically singular matrix.
+bool host_sparse_lu(const HostCsr &A, const int32_t *q, double diag_tol, HostCsr &L, HostCsr &U,
+                    std::vector<int32_t> &p)
+{
+    const int32_t n = A.nrows;
+    const HostCsr Ac = transpose(A);   // row c of Ac = column c of A
+    std::vector<int32_t> pinv((size_t)n, -1), mark((size_t)n, -1), xi((size_t)n), rstack((size_t)n),
+        pstack((size_t)n);
+    std::vector<double> x((size_t)n, 0.0);
+    // factors by columns; L with the original row ids until the end
+    std::vector<int32_t> Lp(1, 0), Li, Up(1, 0), Ui;
+    std::vector<double> Lx, Ux;
+    Li.reserve((size_t)A.nnz() * 4);
+    Lx.reserve((size_t)A.nnz() * 4);
+    Ui.reserve((size_t)A.nnz() * 4);
+    Ux.reserve((size_t)A.nnz() * 4);
+    p.assign((size_t)n, -1);
+    for (int32_t j = 0; j < n; ++j) {
+        const int32_t col = q ? q[j] : j;
+        int32_t top = n;
+        for (int32_t e = Ac.rp[col]; e < Ac.rp[col + 1]; ++e) {
+            const int32_t start = Ac.ci[e];
+            if (mark[start] == j) continue;
+            int32_t head = 0;
+            rstack[0] = start;
+            while (head >= 0) {   // depth-first search, post-order onto xi[top..n)
+                const int32_t i = rstack[head];
+                const int32_t k = pinv[i];
+                if (mark[i] != j) {
+                    mark[i] = j;
+                    pstack[head] = k < 0 ? 0 : Lp[k];
+                }
+                const int32_t pend = k < 0 ? 0 : Lp[k + 1];
+                bool done = true;
+                for (int32_t pp = pstack[head]; pp < pend; ++pp) {
+                    const int32_t r = Li[pp];
+                    if (mark[r] == j) continue;
+                    pstack[head] = pp + 1;
+                    rstack[++head] = r;
+                    done = false;
+                    break;
+                }
+                if (done) {
+                    --head;
+                    xi[--top] = i;
+                }
+            }
+        }
+        for (int32_t e = Ac.rp[col]; e < Ac.rp[col + 1]; ++e) x[Ac.ci[e]] = Ac.v[e];
+        // x = L^-1 A(:, col) in topological order; pivotal rows become U(:, j)
+        double amax = -1.0;
+        int32_t ipiv = -1;
+        for (int32_t px = top; px < n; ++px) {
+            const int32_t i = xi[px];
+            const int32_t k = pinv[i];
+            if (k < 0) {
+                const double a = std::fabs(x[i]);
+                if (a > amax) {
+                    amax = a;
+                    ipiv = i;
+                }
+                continue;
+            }
+            const double xk = x[i];
+            Ui.push_back(k);
+            Ux.push_back(xk);
+            for (int32_t pp = Lp[k] + 1; pp < Lp[k + 1]; ++pp) x[Li[pp]] -= Lx[pp] * xk;
+        }
+        if (ipiv < 0 || !(amax > 0.0)) return false;
+        if (pinv[col] < 0 && mark[col] == j && std::fabs(x[col]) >= diag_tol * amax) ipiv = col;
+        const double pivot = x[ipiv];
+        pinv[ipiv] = j;
+        p[j] = ipiv;
+        Ui.push_back(j);
+        Ux.push_back(pivot);
+        Up.push_back((int32_t)Ui.size());
+        Li.push_back(ipiv);   // unit diagonal first
+        Lx.push_back(1.0);
+        for (int32_t px = top; px < n; ++px) {
+            const int32_t i = xi[px];
+            if (pinv[i] < 0) {
+                Li.push_back(i);
+                Lx.push_back(x[i] / pivot);
+            }
+            x[i] = 0.0;
+        }
+        if (Li.size() > 2000000000u || Ui.size() > 2000000000u)
+            throw std::runtime_error("LU factor exceeds int32 indexing");
+        Lp.push_back((int32_t)Li.size());
+    }
+    for (auto &r : Li) r = pinv[r];
+    HostCsr Lc, Uc;   // the column-wise factors, as "CSR of the transpose"
+    Lc.nrows = Lc.ncols = Uc.nrows = Uc.ncols = n;
+    Lc.rp = std::move(Lp);
+    Lc.ci = std::move(Li);
+    Lc.v = std::move(Lx);
+    Uc.rp = std::move(Up);
+    Uc.ci = std::move(Ui);
+    Uc.v = std::move(Ux);
+    L = transpose(Lc);
+    U = transpose(Uc);
+    return true;
 }
 
 // Up-looking sparse Cholesky driven by the elimination tree (replaces

@@ -47,6 +47,11 @@ int nd_ordering(int32_t n, const int32_t *rp, const int32_t *ci, int32_t *perm);
 // false when a pivot is not positive
 bool host_cholesky(const HostCsr &A, const int32_t *perm, HostCsr &L);
 HostCsr transpose(const HostCsr &A);
+// sparse LU with threshold partial pivoting: P A Q = L U, q given (may be NULL), p returned
+bool host_sparse_lu(const HostCsr &A, const int32_t *q, double diag_tol, HostCsr &L, HostCsr &U,
+                    std::vector<int32_t> &p);
+// fill-reducing ordering of the pattern of A + A^T (METIS_NodeND)
+int nd_ordering_symmetrized(int32_t n, const int32_t *rp, const int32_t *ci, int32_t *perm);
 
 struct RankLayout {
     bool have_index = false, have_matrix = false;

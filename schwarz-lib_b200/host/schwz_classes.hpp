@@ -27,6 +27,7 @@ struct State {
     std::vector<int32_t> factor_perm, L_rowptr, L_col;
     std::vector<double> L_val;
     bool have_factors = false;
+    schwz_lu *lu = nullptr;   // --local_factorization=umfpack: P A Q = L U, Q = factor_perm
     double resnorm = -1.0;
 };
 void check(int rc, const char *file, int line);

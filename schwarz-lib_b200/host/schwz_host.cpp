@@ -212,7 +212,51 @@ void Solve<V, I, M>::setup_local_solver(
     metadata.post_process_data.global_residual_vector_out =
         std::vector<std::vector<V>>(metadata.num_subdomains);
     const auto solver = settings.local_solver;
-    if (solver == Settings::direct_solver_ginkgo || solver == Settings::direct_solver_cholmod) {
+    const bool direct = solver == Settings::direct_solver_ginkgo ||
+                        solver == Settings::direct_solver_cholmod ||
+                        solver == Settings::direct_solver_umfpack;
+    // the unsymmetric factorisation: --local_solver=direct-umfpack, or direct-ginkgo with
+    // --local_factorization=umfpack (source/solve.cpp:145-171, 322-385)
+    const bool want_lu = solver == Settings::direct_solver_umfpack ||
+                         (solver == Settings::direct_solver_ginkgo &&
+                          settings.factorization == "umfpack");
+    if (direct && want_lu) {
+        b200::State &D = *solve_dev_;
+        const int32_t n = (int32_t)metadata.local_size_x;
+        std::vector<int32_t> rp(n + 1), ci(local_matrix->get_num_stored_elements());
+        std::vector<double> v(ci.size());
+        B200_CHECK(schwz_b200_setup_local_matrix(D.setup, metadata.my_rank, rp.data(), ci.data(),
+                                                 v.data()));
+        D.factor_perm.resize(n);
+        if (settings.naturally_ordered_factor)
+            std::iota(D.factor_perm.begin(), D.factor_perm.end(), 0);
+        else
+            B200_CHECK(schwz_b200_host_nd_ordering(n, rp.data(), ci.data(), D.factor_perm.data()));
+        B200_CHECK(schwz_b200_host_lu_create(n, rp.data(), ci.data(), v.data(),
+                                             D.factor_perm.data(), 1e-3, &D.lu));
+        int64_t lnnz = 0, unnz = 0;
+        B200_CHECK(schwz_b200_host_lu_nnz(D.lu, &lnnz, &unnz));
+        if (metadata.my_rank == 0)
+            SAY(" Local direct factorization (sparse LU, threshold partial pivoting, "
+                << (settings.naturally_ordered_factor ? "natural" : "nested dissection")
+                << " column ordering)");
+        SAY(" Process " << metadata.my_rank << " has factors with " << n << " rows and " << lnnz
+                        << " + " << unnz << " non-zeros ");
+        auto host = settings.executor->get_master();
+        triangular_factor_l = gko::matrix::Csr<V, I>::create(host, gko::dim<2>(n), lnnz);
+        triangular_factor_u = gko::matrix::Csr<V, I>::create(host, gko::dim<2>(n), unnz);
+        std::vector<int32_t> rowp(n), tmp_rp(n + 1), tmp_ci(std::max(lnnz, unnz));
+        std::vector<int32_t> tmp_rp2(n + 1), tmp_ci2(std::max(lnnz, unnz));
+        std::vector<double> tmp_v(std::max(lnnz, unnz)), tmp_v2(std::max(lnnz, unnz));
+        B200_CHECK(schwz_b200_host_lu_get(D.lu, tmp_rp.data(), tmp_ci.data(), tmp_v.data(),
+                                          tmp_rp2.data(), tmp_ci2.data(), tmp_v2.data(),
+                                          rowp.data()));
+        local_perm = gko::matrix::Permutation<I>::create(host, std::vector<I>(rowp.begin(), rowp.end()));
+        local_inv_perm = gko::matrix::Permutation<I>::create(
+            host, std::vector<I>(D.factor_perm.begin(), D.factor_perm.end()));
+        if (metadata.my_rank == 0)
+            SAY(" Local direct solve with level-scheduled TRS");
+    } else if (direct) {
         // factorisation on the host (replaces cholmod_analyze / cholmod_factorize,
         // solve.cpp:94-142); fill-reducing order unless --factor_ordering_natural
         b200::State &D = *solve_dev_;
@@ -840,6 +884,11 @@ void SolverRAS<V, I, M>::setup_comm_buffers()
             if (D.have_factors)
                 B200_CHECK(schwz_b200_ras_set_factors(D.ras, D.L_rowptr.data(), D.L_col.data(),
                                                       D.L_val.data(), D.factor_perm.data()));
+            if (D.lu) {
+                B200_CHECK(schwz_b200_ras_set_lu_factors(D.ras, D.lu, D.factor_perm.data()));
+                B200_CHECK(schwz_b200_host_lu_destroy(D.lu));
+                D.lu = nullptr;
+            }
             B200_CHECK(schwz_b200_setup_release_rank(D.setup, me));
             G.slots(kSlotRas)[me] = D.ras;
             G.slots(kSlotCtx)[me] = D.ctx;

@@ -193,6 +193,43 @@ def nd_ordering(rp, ci):
     return perm
 
 
+class HostLu:
+    """Sparse LU with threshold partial pivoting on the host, P A Q = L U (the UMFPACK branch of
+    the reference, source/solve.cpp:145-171, 322-385).  col_perm = Q or None."""
+
+    def __init__(self, rp, ci, v, col_perm=None, diag_pivot_tol=1e-3):
+        rp, ci, v = _i32(rp), _i32(ci), _f64(v)
+        self.n = len(rp) - 1
+        self.col_perm = None if col_perm is None else _i32(col_perm)
+        h = C.c_void_p()
+        _chk(load().schwz_b200_host_lu_create(C.c_int32(self.n), _p(rp), _p(ci), _p(v),
+                                              _p(self.col_perm), C.c_double(diag_pivot_tol),
+                                              C.byref(h)))
+        self.h = h
+
+    def close(self):
+        if self.h:
+            load().schwz_b200_host_lu_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def factors(self):
+        """(L csr triple, U csr triple, row_perm)"""
+        nl, nu = C.c_int64(0), C.c_int64(0)
+        _chk(load().schwz_b200_host_lu_nnz(self.h, C.byref(nl), C.byref(nu)))
+        L = (np.zeros(self.n + 1, np.int32), np.zeros(nl.value, np.int32), np.zeros(nl.value))
+        U = (np.zeros(self.n + 1, np.int32), np.zeros(nu.value, np.int32), np.zeros(nu.value))
+        p = np.zeros(self.n, np.int32)
+        _chk(load().schwz_b200_host_lu_get(self.h, _p(L[0]), _p(L[1]), _p(L[2]), _p(U[0]),
+                                           _p(U[1]), _p(U[2]), _p(p)))
+        return L, U, p
+
+
 class Setup:
     """Index sets of one RAS problem (SolverRAS::setup_local_matrices /
     setup_comm_buffers / setup_windows, source/restricted_schwarz.cpp:56-711).
@@ -614,6 +651,10 @@ class Ras:
         Lrp, Lci, Lv = _i32(Lrp), _i32(Lci), _f64(Lv)
         pp = None if perm is None else _i32(perm)
         _chk(load().schwz_b200_ras_set_factors(self.h, _p(Lrp), _p(Lci), _p(Lv), _p(pp)))
+
+    def set_lu_factors(self, lu):
+        """direct local solve Q U^-1 L^-1 P b with the factors of a HostLu"""
+        _chk(load().schwz_b200_ras_set_lu_factors(self.h, lu.h, _p(lu.col_perm)))
 
     def mailbox(self):
         base = C.c_void_p()
