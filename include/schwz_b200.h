@@ -348,7 +348,7 @@ int schwz_b200_ras_download_solution(schwz_ras *r, double *host_solution_global)
 int schwz_b200_ras_reset(schwz_ras *r);   /* x, init_guess <- 0, norms unlatched */
 /* measurement aid: average duration of one launch of a hot kernel on this
  * subdomain's data (CUDA events on its stream) and its algorithmic bytes.
- * kind: 0 SpMV+dot of CG, 1 CG x/r update, 2 CG p update, 3 residual
+ * kind: 0 SpMV+dot of CG, 1 CG r update, 2 CG x/p update, 3 residual
  * SpMV+norm, 4 halo push+unpack, 5 push only, 6 unpack only (call 5 and 6 with
  * the same reps: they advance the exchange epoch) */
 int schwz_b200_ras_kernel_time(schwz_ras *r, int32_t kind, int32_t reps, float *ms);

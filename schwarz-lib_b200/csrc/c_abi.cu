@@ -963,8 +963,8 @@ int64_t schwz_b200_ras_kernel_bytes(schwz_ras *r, int32_t kind)
     const int64_t n = R.local_size_x, nnz = R.local_nnz;
     switch (kind) {
     case 0: return 12 * nnz + 4 * (n + 1) + 8 * n + 8 * n;            // val+col, rowptr, q, p
-    case 1: return 48 * n;                                            // x,r,p,q read; x,r write
-    case 2: return 24 * n;                                            // r,p read; p write
+    case 1: return 24 * n;                                            // r,q read; r write
+    case 2: return 40 * n;                                            // r,p,x read; p,x write
     case 3: return 12 * nnz + 4 * (n + 1) + 8 * n + 8 * n + 8 * n;    // + rhs read
     case 4: {                                                         // push + unpack: 20 B/element
         int64_t e = 0;

@@ -83,7 +83,8 @@ DeviceCsr *csr_upload(const Ctx &ctx, int32_t nrows, int32_t ncols, const int32_
 // scalars of one device-resident Krylov solve
 struct CgScalars {
     double rho, prev_rho, beta, r0, resnorm, tol;
-    int32_t iter, stop, max_iters, pad;
+    int32_t iter, stop, max_iters, pending;   // pending: x += alpha * p not applied yet
+    double alpha;
 };
 
 enum SpmvEpilogue { EPI_NONE = 0, EPI_DOT = 1, EPI_NRM2SQ = 2, EPI_NRM2 = 3 };
@@ -109,9 +110,11 @@ void launch_permute(const Ctx &ctx, int32_t n, const int32_t *perm, int inverse,
 // CG step kernels (Ginkgo Cg semantics)
 void launch_cg_init(const Ctx &ctx, CgScalars *s, int32_t max_iters, double tol,
                     const int32_t *outer_stop);
-void launch_cg_p_update(const Ctx &ctx, int64_t n, const double *r, double *p, const CgScalars *s);
-void launch_cg_xr_update(const Ctx &ctx, int64_t n, double *x, double *r, const double *p,
-                         const double *q, CgScalars *s, bool precond = false);
+void launch_cg_xp_update(const Ctx &ctx, int64_t n, const double *r_or_z, double *p, double *x,
+                         const CgScalars *s);
+void launch_cg_r_update(const Ctx &ctx, int64_t n, double *r, const double *q, CgScalars *s,
+                        bool precond = false);
+void launch_cg_flush_x(const Ctx &ctx, int64_t n, double *x, const double *p, const CgScalars *s);
 
 // halo
 void launch_halo_pack_push(const Ctx &ctx, int32_t nseg, const int32_t *seg_off_dev,

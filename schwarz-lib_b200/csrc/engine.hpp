@@ -85,7 +85,7 @@ public:
                const int32_t *outer_stop = nullptr);
     void result(int32_t *iters, double *resnorm, double *resnorm0);   // synchronises
     int64_t bytes_per_iteration() const;
-    void bench_step(int kind, double *scratch_x);   // 1: x/r update, 2: p update (timing only)
+    void bench_step(int kind, double *scratch_x);   // 1: r update, 2: x/p update (timing only)
 
 private:
     void iteration(double *x);
@@ -242,7 +242,7 @@ public:
     void reset_state();                                      // x, init_guess <- 0; norms unlatched
     // average duration (ms) of one launch of a hot kernel on this subdomain's
     // data, CUDA events on the subdomain's stream: 0 SpMV+dot (CG q = A p),
-    // 1 x/r update, 2 p update, 3 residual SpMV+norm, 4 halo push+unpack, 5 push, 6 unpack
+    // 1 CG r update, 2 CG x/p update, 3 residual SpMV+norm, 4 halo push+unpack, 5 push, 6 unpack
     float kernel_time_ms(int kind, int reps);
 
     const Ctx &ctx;

@@ -123,6 +123,8 @@ __global__ void __launch_bounds__(kSmallThreads, 1)
         out->tol = tol;
         out->iter = iter;
         out->max_iters = max_iters;
+        out->pending = 0;
+        out->alpha = 0.0;
         out->stop = 1;
     }
 }

@@ -48,9 +48,9 @@ void CgSolver::set_precond(Preconditioner *M)
 
 int64_t CgSolver::bytes_per_iteration() const
 {
-    // SpMV (q = A p, p.q fused) + x/r update (4 reads, 2 writes) + p update
-    // (2 reads, 1 write): SURVEY.md 8(d) minus the traffic the fusion removes
-    return 12 * A_.nnz + 4 * (n_ + 1) + 16 * n_ + 48 * n_ + 24 * n_ +
+    // SpMV (q = A p, p.q fused) + r update (2 reads, 1 write) + x/p update (3 reads,
+    // 2 writes): SURVEY.md 8(d) minus the traffic the fusions remove
+    return 12 * A_.nnz + 4 * (n_ + 1) + 16 * n_ + 24 * n_ + 40 * n_ +
            (M_ ? M_->bytes_per_apply() : 0);
 }
 
@@ -61,13 +61,13 @@ void CgSolver::iteration(double *x)
         // only produces ||r|| for the stop test (which Ginkgo evaluates after rho, before
         // the p update - the order of the two does not change any number)
         M_->apply(r_, z_, &s_->rho, &s_->stop);
-        launch_cg_p_update(ctx_, n_, z_, p_, s_);
+        launch_cg_xp_update(ctx_, n_, z_, p_, x, s_);
     } else {
-        launch_cg_p_update(ctx_, n_, r_, p_, s_);
+        launch_cg_xp_update(ctx_, n_, r_, p_, x, s_);
     }
     launch_spmv(ctx_, A_, 1.0, p_, 0.0, nullptr, q_, EPI_DOT, p_, &s_->beta, (int32_t)n_,
                 &s_->stop);
-    launch_cg_xr_update(ctx_, n_, x, r_, p_, q_, s_, M_ != nullptr);
+    launch_cg_r_update(ctx_, n_, r_, q_, s_, M_ != nullptr);
 }
 
 void CgSolver::solve(const double *b, double *x, int32_t max_iters, double tol,
@@ -85,6 +85,7 @@ void CgSolver::solve(const double *b, double *x, int32_t max_iters, double tol,
     launch_cg_init(ctx_, s_, max_iters, tol, outer_stop);
     if (max_iters <= kCgNoPoll) {
         for (int it = 0; it < max_iters; ++it) iteration(x);
+        launch_cg_flush_x(ctx_, n_, x, p_, s_);
         return;
     }
     int done = 0, chunk = 0;
@@ -103,6 +104,7 @@ void CgSolver::solve(const double *b, double *x, int32_t max_iters, double tol,
         }
         ++chunk;
     }
+    launch_cg_flush_x(ctx_, n_, x, p_, s_);
 }
 
 void CgSolver::bench_step(int kind, double *scratch_x)
@@ -117,11 +119,15 @@ void CgSolver::bench_step(int kind, double *scratch_x)
         SCHWZ_CUDA(cudaMemcpyAsync(&s_->max_iters, &cap, sizeof(cap), cudaMemcpyHostToDevice, ctx_.stream));
         SCHWZ_CUDA(cudaMemcpyAsync(&s_->tol, &tol, sizeof(tol), cudaMemcpyHostToDevice, ctx_.stream));
         SCHWZ_CUDA(cudaMemcpyAsync(&s_->stop, &zero, sizeof(zero), cudaMemcpyHostToDevice, ctx_.stream));
+        // a pending x update with alpha = 0: the x/p kernel streams x as in a live iteration
+        const int32_t one = 1;
+        SCHWZ_CUDA(cudaMemcpyAsync(&s_->pending, &one, sizeof(one), cudaMemcpyHostToDevice, ctx_.stream));
+        SCHWZ_CUDA(cudaMemcpyAsync(&s_->alpha, &tol, sizeof(tol), cudaMemcpyHostToDevice, ctx_.stream));
         SCHWZ_CUDA(cudaStreamSynchronize(ctx_.stream));
         return;
     }
-    if (kind == 1) launch_cg_xr_update(ctx_, n_, scratch_x, r_, p_, q_, s_, false);
-    else launch_cg_p_update(ctx_, n_, r_, p_, s_);
+    if (kind == 1) launch_cg_r_update(ctx_, n_, r_, q_, s_, false);
+    else launch_cg_xp_update(ctx_, n_, r_, p_, scratch_x, s_);
 }
 
 void CgSolver::result(int32_t *iters, double *resnorm, double *resnorm0)
