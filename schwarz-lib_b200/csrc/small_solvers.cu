@@ -161,13 +161,15 @@ void launch_cg_small(const Ctx &ctx, const DeviceCsr &A, const double *b, double
 // -----------------------------------------------------------------------------
 template <int kSmallThreads>
 __global__ void __launch_bounds__(kSmallThreads, 1)
-    gmres_small_kernel(int32_t n, const int32_t *__restrict__ rp, const int32_t *__restrict__ ci,
-                       const double *__restrict__ v, const double *__restrict__ b, double *x,
+    gmres_small_kernel(int32_t n, const int32_t *__restrict__ rp_g, const int32_t *__restrict__ ci_g,
+                       const double *__restrict__ v_g, const double *__restrict__ b, double *x,
                        double *V, int32_t m, int32_t max_iters, double tol, double *resnorm_out,
-                       double *r0_out, int32_t *total_out, int basis_in_smem)
+                       double *r0_out, int32_t *total_out, int basis_in_smem, int matrix_in_smem)
 {
     extern __shared__ __align__(16) double sm[];
     int phase = 0;
+    const int32_t *rp = rp_g, *ci = ci_g;
+    const double *v = v_g;
     double *w = sm;                               // n
     double *H = w + n;                            // (m+1)*m, column-major
     double *cs = H + (size_t)(m + 1) * m;         // m
@@ -175,8 +177,28 @@ __global__ void __launch_bounds__(kSmallThreads, 1)
     double *g = sn + m;                           // m+1
     double *y = g + m + 1;                        // m
     double *buf = y + m;                          // kSmallBuf
-    if (basis_in_smem) V = buf + kSmallBuf;       // (m+1)*n
+    double *tail = buf + kSmallBuf;
+    if (basis_in_smem) {
+        V = tail;                                 // (m+1)*n
+        tail += (size_t)(m + 1) * n;
+    }
     const int t = threadIdx.x;
+    if (matrix_in_smem) {
+        // the matrix is read once per Arnoldi step: keep it next to the vectors (with the
+        // shared-memory carve-out this large, little L1 is left for it)
+        const int32_t nnz = rp_g[n];
+        double *sv = tail;                                   // nnz
+        int32_t *sci = reinterpret_cast<int32_t *>(sv + nnz);   // nnz
+        int32_t *srp = sci + nnz;                            // n + 1
+        for (int32_t k = t; k < nnz; k += kSmallThreads) {
+            sv[k] = v_g[k];
+            sci[k] = ci_g[k];
+        }
+        for (int32_t k = t; k <= n; k += kSmallThreads) srp[k] = rp_g[k];
+        rp = srp;
+        ci = sci;
+        v = sv;
+    }
 
     // r = b - A x ; ||r|| ; V0 = r / ||r||   (x read from global: it changes at restarts)
     auto begin_cycle = [&]() -> double {
@@ -184,7 +206,7 @@ __global__ void __launch_bounds__(kSmallThreads, 1)
         double part = 0.0;
         for (int32_t i = t; i < n; i += kSmallThreads) {
             double acc = b[i];
-            for (int32_t k = rp[i]; k < rp[i + 1]; ++k) acc += (-__ldg(v + k)) * x[__ldg(ci + k)];
+            for (int32_t k = rp[i]; k < rp[i + 1]; ++k) acc += (-v[k]) * x[ci[k]];
             w[i] = acc;
             part += acc * acc;
         }
@@ -232,7 +254,7 @@ __global__ void __launch_bounds__(kSmallThreads, 1)
         const double *vk = V + (size_t)k * n;
         for (int32_t i = t; i < n; i += kSmallThreads) {
             double acc = 0.0;
-            for (int32_t q = rp[i]; q < rp[i + 1]; ++q) acc += __ldg(v + q) * vk[__ldg(ci + q)];
+            for (int32_t q = rp[i]; q < rp[i + 1]; ++q) acc += v[q] * vk[ci[q]];
             w[i] = acc;
         }
         double *col = H + (size_t)k * (m + 1);
@@ -284,10 +306,12 @@ __global__ void __launch_bounds__(kSmallThreads, 1)
     }
 }
 
-static size_t gmres_small_smem(int64_t n, int m, bool basis)
+static size_t gmres_small_smem(int64_t n, int m, bool basis, int64_t nnz_in_smem = -1)
 {
-    return ((size_t)n + (size_t)(m + 1) * m + 4 * (size_t)m + 1 + kSmallBuf + 8 +
-            (basis ? (size_t)(m + 1) * n : 0)) * sizeof(double);
+    size_t bytes = ((size_t)n + (size_t)(m + 1) * m + 4 * (size_t)m + 1 + kSmallBuf + 8 +
+                    (basis ? (size_t)(m + 1) * n : 0)) * sizeof(double);
+    if (nnz_in_smem >= 0) bytes += 12 * (size_t)nnz_in_smem + 4 * ((size_t)n + 1) + 16;
+    return bytes;
 }
 
 bool gmres_small_fits(int64_t n, int m)
@@ -308,12 +332,13 @@ void launch_gmres_small(const Ctx &ctx, const DeviceCsr &A, const double *b, dou
         configured[ctx.device] = true;
     }
     const bool basis = gmres_small_smem(A.nrows, m, true) <= 220 * 1024;
+    const bool matrix = gmres_small_smem(A.nrows, m, basis, A.nnz) <= 220 * 1024;
     const int th = small_threads(A.nrows);
     auto *k = th == 128 ? gmres_small_kernel<128> : th == 256 ? gmres_small_kernel<256>
                                                               : gmres_small_kernel<1024>;
-    k<<<1, th, gmres_small_smem(A.nrows, m, basis), ctx.stream>>>(
+    k<<<1, th, gmres_small_smem(A.nrows, m, basis, matrix ? A.nnz : -1), ctx.stream>>>(
         A.nrows, A.rp, A.ci, A.v, b, x, V, m, max_iters, tol, resnorm_out, r0_out, total_out,
-        basis ? 1 : 0);
+        basis ? 1 : 0, matrix ? 1 : 0);
     SCHWZ_CUDA(cudaGetLastError());
     count_launch();
 }

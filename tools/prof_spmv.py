@@ -20,7 +20,7 @@ sub.update_boundary()
 sub.local_residual()
 sub.local_solve()
 sub.sync()
-for kind, name in ((0, "spmv+dot"), (3, "residual spmv+norm"), (1, "cg x/r update"), (2, "cg p update")):
+for kind, name in ((0, "spmv+dot"), (3, "residual spmv+norm"), (1, "cg r update"), (2, "cg x/p update")):
     ms = sub.kernel_time_ms(kind, reps)
     b = sub.kernel_bytes(kind)
     print("%-20s %8.3f us  %8.1f GB/s  (%d bytes)" % (name, ms * 1e3, b / ms / 1e6, b))
