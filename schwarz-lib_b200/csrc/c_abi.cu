@@ -70,6 +70,8 @@ int schwz_b200_ctx_create(int device, schwz_ctx **out)
     if (vr) g_spmv_variant = std::atoi(vr);
     const char *ns = std::getenv("SCHWZ_B200_NO_SMALL");
     g_use_small_solvers = !(ns && ns[0] == '1');
+    const char *ng = std::getenv("SCHWZ_B200_NO_CG_GRAPH");
+    g_use_cg_graph = !(ng && ng[0] == '1');
     *out = new schwz_ctx(device);
     ABI_END
 }

@@ -23,6 +23,7 @@ Comm *comm_create(const Ctx &ctx, const void *id128, int nranks, int rank);
 void comm_allgather_f64(Comm &c, const double *dev_in, int count, double *dev_out);
 
 // one-CTA solvers for small subdomains (small_solvers.cu)
+extern bool g_use_cg_graph;        // SCHWZ_B200_NO_CG_GRAPH=1 turns the CG graph replay off
 extern bool g_use_small_solvers;   // SCHWZ_B200_NO_SMALL=1 turns them off (A/B measurements)
 bool cg_small_fits(int64_t n);
 void launch_cg_small(const Ctx &ctx, const DeviceCsr &A, const double *b, double *x,
@@ -97,6 +98,18 @@ private:
     CgScalars *s_ = nullptr;
     int32_t *pinned_stop_ = nullptr;   // 2 slots
     cudaEvent_t ev_[2] = {nullptr, nullptr};
+    // the captured launch sequence of a whole solve (fixed buffers, fixed budget)
+    struct Captured {
+        const double *b;
+        double *x;
+        int32_t max_iters;
+        double tol;
+        const int32_t *outer_stop;
+        cudaGraphExec_t exec;
+        int launches;
+    };
+    std::vector<Captured> graphs_;
+    int plain_solves_ = 0;
 };
 
 // ---- GMRES(m) (Ginkgo Gmres semantics; source/solve.cpp:486-567) -------------

@@ -13,6 +13,7 @@ namespace schwz_b200 {
 // CG
 // =============================================================================
 bool g_use_small_solvers = true;
+bool g_use_cg_graph = true;   // SCHWZ_B200_NO_CG_GRAPH=1 turns the graph replay off (A/B)
 
 constexpr int kCgNoPoll = 160;   // up to this many iterations: enqueue all, never poll
 constexpr int kCgChunk = 32;     // otherwise poll the stop flag once per chunk
@@ -38,10 +39,13 @@ CgSolver::~CgSolver()
     if (pinned_stop_) cudaFreeHost(pinned_stop_);
     for (auto &e : ev_)
         if (e) cudaEventDestroy(e);
+    for (const Captured &c : graphs_) cudaGraphExecDestroy(c.exec);
 }
 
 void CgSolver::set_precond(Preconditioner *M)
 {
+    for (const Captured &c : graphs_) cudaGraphExecDestroy(c.exec);
+    graphs_.clear();
     M_ = M;
     if (M_ && !z_) z_ = ctx_.alloc_zero<double>(n_);
 }
@@ -79,15 +83,53 @@ void CgSolver::solve(const double *b, double *x, int32_t max_iters, double tol,
         launch_cg_small(ctx_, A_, b, x, max_iters, tol, s_, outer_stop);
         return;
     }
+    auto enqueue_all = [&]() {
+        // r = b - A x, rho = r.r fused
+        launch_spmv(ctx_, A_, -1.0, x, 1.0, b, r_, EPI_NRM2SQ, nullptr, &s_->rho, (int32_t)n_,
+                    outer_stop);
+        launch_cg_init(ctx_, s_, max_iters, tol, outer_stop);
+        for (int it = 0; it < max_iters; ++it) iteration(x);
+        launch_cg_flush_x(ctx_, n_, x, p_, s_);
+    };
+    if (max_iters <= kCgNoPoll) {
+        // The whole solve is a fixed launch sequence on fixed buffers (the stop decisions are
+        // device flags), so from the second call on it is replayed as ONE CUDA graph: at
+        // mid-size subdomains (10^5..10^6 rows, kernels of a few microseconds) the 3*max_iters
+        // launches are otherwise bound by launch latency.  Not with the ILU preconditioner,
+        // whose triangular solves are graphs of their own.
+        const bool graphable = g_use_cg_graph && (!M_ || M_->kind() != PRECOND_ILU);
+        if (!graphable || ++plain_solves_ < 2) {
+            enqueue_all();
+            return;
+        }
+        for (const Captured &c : graphs_)
+            if (c.b == b && c.x == x && c.max_iters == max_iters && c.tol == tol &&
+                c.outer_stop == outer_stop) {
+                SCHWZ_CUDA(cudaGraphLaunch(c.exec, ctx_.stream));
+                count_launch(c.launches);
+                return;
+            }
+        if (graphs_.size() >= 2) {
+            cudaGraphExecDestroy(graphs_.front().exec);
+            graphs_.erase(graphs_.begin());
+        }
+        ctx_.use();
+        const int64_t before = g_launches.load();
+        cudaGraph_t graph = nullptr;
+        SCHWZ_CUDA(cudaStreamBeginCapture(ctx_.stream, cudaStreamCaptureModeThreadLocal));
+        enqueue_all();
+        SCHWZ_CUDA(cudaStreamEndCapture(ctx_.stream, &graph));
+        Captured c{b, x, max_iters, tol, outer_stop, nullptr, (int)(g_launches.load() - before)};
+        SCHWZ_CUDA(cudaGraphInstantiate(&c.exec, graph, 0));
+        cudaGraphDestroy(graph);
+        graphs_.push_back(c);
+        SCHWZ_CUDA(cudaGraphLaunch(c.exec, ctx_.stream));
+        return;
+    }
     // r = b - A x, rho = r.r fused
     launch_spmv(ctx_, A_, -1.0, x, 1.0, b, r_, EPI_NRM2SQ, nullptr, &s_->rho, (int32_t)n_,
                 outer_stop);
     launch_cg_init(ctx_, s_, max_iters, tol, outer_stop);
-    if (max_iters <= kCgNoPoll) {
-        for (int it = 0; it < max_iters; ++it) iteration(x);
-        launch_cg_flush_x(ctx_, n_, x, p_, s_);
-        return;
-    }
     int done = 0, chunk = 0;
     pinned_stop_[0] = pinned_stop_[1] = 0;
     while (done < max_iters) {
