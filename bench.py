@@ -175,22 +175,18 @@ _CPU_CACHE = {}
 
 
 def cpu_sample(args, steps=1):
-    """One bounded sample = the local solve of ONE of the `subdomains` strips
-    (local_max_iters CG iterations on its local matrix) plus its residual-check
-    SpMV, with every host core; an outer iteration costs `subdomains` of those,
-    so iters/s = 1 / (subdomains * t_sample).  Input: the strip's local CSR as
-    produced by the product's host setup (bit-identical to the oracle's,
-    tests/test_setup.py)."""
+    """One bounded sample = the local-solve work of one outer iteration (per strip: the
+    residual-check SpMV + local_max_iters CG iterations on its local matrix) on every host
+    core, either all cores on one strip after the other or the strips side by side (both are
+    tried once, the faster is kept).  Input: the local CSRs as produced by the product's host
+    setup (bit-identical to the oracle's, tests/test_setup.py).  cfg3 steps the oracle's own
+    RAS loop instead."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle as O
     import schwz_b200 as S
     cores = O.max_threads()
-    # large strips: every core works on one strip, an outer iteration is `subdomains` of those.
-    # tiny subdomains (ani4): one core per subdomain, `cores` subdomains side by side, the way
-    # the reference's MPI ranks would run
     tiny = args.matrix == "ani4"
     O.set_threads(1 if tiny else cores)
-    rounds = args.subdomains
     if tiny:
         # the whole problem is tiny: step the oracle's own RAS loop (all subdomains one after the
         # other on one core) and divide by the number of subdomains that would run side by side
@@ -214,28 +210,63 @@ def cpu_sample(args, steps=1):
                           "%.3g s each with the %d subdomains solved one after the other on one "
                           "core, divided by %d (one core per subdomain, as the reference's MPI "
                           "ranks run)" % (steps, t_seq, args.subdomains, side_by_side)}, t
+    # Large strips.  Two ways to put every host core to work, both timed once, the faster one
+    # kept for the remaining samples:
+    #  A "team":  all cores work on ONE strip (OpenMP inside the SpMV / vector loops); an outer
+    #             iteration is `subdomains` of those, one after the other;
+    #  B "ranks": min(subdomains, cores) strips side by side, cores/that many threads each - the
+    #             way the reference's MPI ranks (x OpenMP threads) occupy a node.
     key = (args.matrix, args.dim, args.n, args.subdomains)
     if key not in _CPU_CACHE:
         setup = make_setup(args, S)
-        r = min(1, args.subdomains - 1)          # an interior strip when there is one
-        _CPU_CACHE[key] = setup.local_matrix(r)
+        conc = min(args.subdomains, cores)
+        mats = []
+        for r in range(conc):
+            mats.append(setup.local_matrix(r))
+            setup.release(r)
+        _CPU_CACHE[key] = {"mats": mats, "x": [np.zeros(len(m[0]) - 1) for m in mats],
+                           "strategy": None}
         del setup
-    rp, ci, v = _CPU_CACHE[key]
-    n = len(rp) - 1
-    b = np.ones(n)
-    x = np.zeros(n)
-    times = []
-    for _ in range(steps):
+    C_ = _CPU_CACHE[key]
+    mats, xs = C_["mats"], C_["x"]
+    conc = len(mats)
+    interior = min(1, conc - 1)                  # an interior strip when there is one
+
+    def one(i):
+        rp, ci, v = mats[i]
+        b = np.ones(len(rp) - 1)
+        O.spmv(rp, ci, v, xs[i], -1.0, 1.0, b)                           # residual check (A10)
+        xs[i], _ = O.cg(rp, ci, v, b, xs[i], args.local_iters, 1e-12)    # local solve (A12)
+
+    def team():
+        O.set_threads(cores)
         t0 = time.perf_counter()
-        O.spmv(rp, ci, v, x, -1.0, 1.0, b)                       # residual check (A10)
-        x, it = O.cg(rp, ci, v, b, x, args.local_iters, 1e-12)   # local solve (A12)
-        times.append(time.perf_counter() - t0)
+        one(interior)
+        return (time.perf_counter() - t0) * args.subdomains
+
+    def ranks():
+        from concurrent.futures import ThreadPoolExecutor
+        O.set_threads(max(1, cores // conc))
+        t0 = time.perf_counter()
+        with ThreadPoolExecutor(conc) as ex:
+            list(ex.map(one, range(conc)))
+        return (time.perf_counter() - t0) * (-(-args.subdomains // conc))
+
+    if C_["strategy"] is None:
+        ta, tb = team(), ranks()
+        C_["strategy"] = "team" if ta <= tb else "ranks"
+        C_["first"] = {"team_s_per_outer": ta, "ranks_s_per_outer": tb}
+    times = [team() if C_["strategy"] == "team" else ranks() for _ in range(steps)]
     t = float(np.median(times))
-    value = 1.0 / (rounds * t)
-    return {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "_t": t,
-            "sample": "1 of %d strips: residual SpMV + %d CG iterations on its %d-row local "
-                      "matrix, %.3g s per sample, all cores on the strip, scaled x%d"
-                      % (args.subdomains, args.local_iters, n, t, rounds)}, t
+    n = len(mats[interior][0]) - 1
+    how = ("all %d cores on one strip, x%d strips" % (cores, args.subdomains)
+           if C_["strategy"] == "team" else
+           "%d strips side by side with %d thread(s) each" % (conc, max(1, cores // conc)))
+    return {"value": 1.0 / t, "unit": UNIT, "cores": cores, "kind": "port", "_t": t,
+            "sample": "residual SpMV + %d CG iterations on the %d-row local matrices of one outer "
+                      "iteration: %s, %.3g s per outer iteration (first try: team %.3g s, ranks "
+                      "%.3g s)" % (args.local_iters, n, how, t, C_["first"]["team_s_per_outer"],
+                                   C_["first"]["ranks_s_per_outer"])}, t
 
 
 def run_reference(args):
