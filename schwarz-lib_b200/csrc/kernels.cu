@@ -884,8 +884,7 @@ __global__ void __launch_bounds__(kBlock)
     halo_pack_push_kernel(int32_t nseg, const int32_t *__restrict__ seg_off, int32_t total,
                           const int32_t *__restrict__ src_idx, const double *__restrict__ x,
                           void *const *__restrict__ dst_ptrs,
-                          unsigned long long *const *__restrict__ flag_ptrs,
-                          unsigned long long epoch, unsigned int *ticket, const int32_t *stop)
+                          const int32_t *stop)
 {
     __shared__ int32_t s_off[kMaxSeg + 1];
     __shared__ T *s_dst[kMaxSeg];
@@ -898,26 +897,20 @@ __global__ void __launch_bounds__(kBlock)
         while (e >= s_off[s + 1]) ++s;
         s_dst[s][e - s_off[s]] = (T)x[src_idx[e]];
     }
-    if (flag_ptrs != nullptr) {
-        // One system-scope fence per CTA, issued by the thread that then takes the ticket: the
-        // barrier makes the CTA's peer stores happen-before it, the fence is cumulative.  (With
-        // a fence in every thread the cfg2 push took 14.0 us, with this 11.6 us; what remains is
-        // mostly the system-scope fences themselves - the unpack of the same 32 K elements, which
-        // has none, takes 3.9 us.)
-        __shared__ int s_last;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            __threadfence_system();
-            const unsigned int tk = atomicAdd(ticket, 1u);
-            s_last = (tk == gridDim.x - 1);
-            if (s_last) *ticket = 0u;   // re-arm for the next launch
-        }
-        __syncthreads();
-        if (s_last && threadIdx.x < nseg) {
-            __threadfence_system();
-            st_release_sys(flag_ptrs[threadIdx.x], epoch);
-        }
-    }
+}
+
+// Publishes the epoch to every out-neighbour's flag word (the replacement for MPI_Win_flush +
+// a flag Put).  Its own launch, right behind the pack/push kernel on the same stream: the
+// kernel boundary orders all of that grid's peer stores before this one, and the release store
+// is cumulative, so no thread of the data kernel has to execute a system-scope fence.  (ncu,
+// cfg2: pack/push 5.7 us, publish 6.5 us with fence + release store; with a fence in every
+// thread of the data kernel the single-kernel version took 14.0 us.  A system-scope release
+// costs microseconds on this platform whoever issues it.)
+__global__ void halo_publish_kernel(int32_t nseg, unsigned long long *const *__restrict__ flag_ptrs,
+                                    unsigned long long epoch, const int32_t *stop)
+{
+    if (stop != nullptr && *stop != 0) return;
+    if ((int)threadIdx.x < nseg) st_release_sys(flag_ptrs[threadIdx.x], epoch);
 }
 
 void launch_halo_pack_push(const Ctx &ctx, int32_t nseg, const int32_t *seg_off_dev,
@@ -930,13 +923,17 @@ void launch_halo_pack_push(const Ctx &ctx, int32_t nseg, const int32_t *seg_off_
     ctx.use();
     int grid = std::max(1, std::min((total + kBlock - 1) / kBlock, kVecGrid));
     if (f32)
-        halo_pack_push_kernel<float><<<grid, kBlock, 0, ctx.stream>>>(
-            nseg, seg_off_dev, total, src_idx, x, dst_ptrs, flag_ptrs, epoch, ctx.tickets + 3, stop);
+        halo_pack_push_kernel<float><<<grid, kBlock, 0, ctx.stream>>>(nseg, seg_off_dev, total,
+                                                                      src_idx, x, dst_ptrs, stop);
     else
-        halo_pack_push_kernel<double><<<grid, kBlock, 0, ctx.stream>>>(
-            nseg, seg_off_dev, total, src_idx, x, dst_ptrs, flag_ptrs, epoch, ctx.tickets + 3, stop);
-    SCHWZ_CUDA(cudaGetLastError());
+        halo_pack_push_kernel<double><<<grid, kBlock, 0, ctx.stream>>>(nseg, seg_off_dev, total,
+                                                                       src_idx, x, dst_ptrs, stop);
     count_launch();
+    if (flag_ptrs != nullptr) {
+        halo_publish_kernel<<<1, kMaxSeg, 0, ctx.stream>>>(nseg, flag_ptrs, epoch, stop);
+        count_launch();
+    }
+    SCHWZ_CUDA(cudaGetLastError());
 }
 
 // Unpack for ALL in-neighbours in one launch (Scatter copy,
