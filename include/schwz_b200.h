@@ -268,6 +268,10 @@ int schwz_b200_ras_destroy(schwz_ras *r);
 int schwz_b200_ras_set_factors(schwz_ras *r, const int32_t *L_rowptr,
                                const int32_t *L_col, const double *L_val,
                                const int32_t *perm);
+/* the cap of the iterative local solve from now on (-1 = local_size_x): what re-building the
+ * stopping criterion with metadata.updated_max_iters past settings.reset_local_crit_iter does
+ * (source/solve.cpp:721-741) */
+int schwz_b200_ras_set_local_max_iters(schwz_ras *r, int32_t local_max_iters);
 /* direct variant, unsymmetric: the factors of schwz_b200_host_lu_create and the column order it
  * was given; local solve = Q U^-1 L^-1 P b (local_perm = P, local_inv_perm = Q of
  * source/solve.cpp:342-353) */
@@ -358,6 +362,10 @@ int schwz_b200_ras_true_residual_sq(schwz_ras *r, double *host_out);
 /* decentralised convergence flags (include/conv_tools.hpp:213-275) */
 int schwz_b200_ras_conv_set_local(schwz_ras *r, int32_t converged_all_local);
 int schwz_b200_ras_conv_forward(schwz_ras *r);
+/* accumulate variant (include/conv_tools.hpp:230-247, --enable_decentralized_accumulate): adds 1
+ * to word 0 of every subdomain's flags while locally converged; needs every subdomain's flags
+ * connected (schwz_b200_ras_connect_conv / _connect_local); conv_count returns word 0 */
+int schwz_b200_ras_conv_accumulate(schwz_ras *r, int32_t converged_all_local);
 /* centralised binary tree (include/conv_tools.hpp:147-209): push up to the parent once the
  * children have, the root pushes down; conv_count then returns P or 0 */
 int schwz_b200_ras_conv_tree(schwz_ras *r, int32_t converged_all_local);
@@ -372,7 +380,7 @@ typedef struct {
     double tolerance;
     int32_t enable_onesided;       /* async: no waits, decentralised flags */
     int32_t enable_global_check;
-    int32_t conv_decentralized;    /* else centralised tree               */
+    int32_t conv_decentralized;    /* 0 centralised tree, 1 flag flooding, 2 accumulate */
     int32_t iter_offset;
     int32_t exchange_mode;         /* one-sided only, see schwz_b200_ras_set_exchange_mode */
     /* cross-process allgather of the residual norms (ncclAllGather); NULL when

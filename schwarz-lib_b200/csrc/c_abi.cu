@@ -708,6 +708,12 @@ int schwz_b200_ras_set_factors(schwz_ras *r, const int32_t *Lrp, const int32_t *
     r->impl->set_factors(Lrp, Lci, Lv, perm);
     ABI_END
 }
+int schwz_b200_ras_set_local_max_iters(schwz_ras *r, int32_t local_max_iters)
+{
+    ABI_BEGIN
+    r->impl->opt.local_max_iters = local_max_iters;
+    ABI_END
+}
 int schwz_b200_ras_set_lu_factors(schwz_ras *r, const schwz_lu *lu, const int32_t *col_perm)
 {
     ABI_BEGIN
@@ -995,6 +1001,12 @@ int schwz_b200_ras_conv_tree(schwz_ras *r, int32_t converged_all_local)
     r->impl->conv_tree(converged_all_local);
     ABI_END
 }
+int schwz_b200_ras_conv_accumulate(schwz_ras *r, int32_t converged_all_local)
+{
+    ABI_BEGIN
+    r->impl->conv_accumulate(converged_all_local);
+    ABI_END
+}
 int schwz_b200_ras_conv_forward(schwz_ras *r)
 {
     ABI_BEGIN
@@ -1027,6 +1039,7 @@ int schwz_b200_ras_run(schwz_ras **subs, int32_t n_local, const schwz_loop_optio
     lo.iter_offset = o->iter_offset;
     lo.exchange_mode = o->exchange_mode;
     lo.conv_tree = (o->enable_onesided && !o->conv_decentralized) ? 1 : 0;
+    lo.conv_accumulate = (o->enable_onesided && o->conv_decentralized == 2) ? 1 : 0;
     lo.comm = o->comm ? o->comm->impl.get() : nullptr;
     LoopResult lr;
     ras_run(v, lo, lr, history);

@@ -140,4 +140,8 @@ void launch_conv_forward(const Ctx &ctx, int32_t P, int32_t me, int32_t converge
 void launch_conv_tree(const Ctx &ctx, int32_t P, int32_t me, int32_t converged_all_local,
                       int32_t *conv, int32_t *const *peer_conv, int32_t *num_converged);
 
+// accumulate variant of the decentralised check (include/conv_tools.hpp:230-247)
+void launch_conv_accumulate(const Ctx &ctx, int32_t P, int32_t me, int32_t converged_all_local,
+                            int32_t *conv, int32_t *const *peer_conv, int32_t *num_converged);
+
 }  // namespace schwz_b200

@@ -594,6 +594,17 @@ void Ras::conv_forward(int32_t converged_all_local)
                         (int32_t)nbr_out.size(), out_conv_dev_, num_converged_dev);
 }
 
+void Ras::conv_accumulate(int32_t converged_all_local)
+{
+    for (int32_t q = 0; q < P; ++q)
+        SCHWZ_REQUIRE(conv_peer_host_[q] != nullptr,
+                      "accumulate convergence check: every subdomain's flags must be connected "
+                      "(schwz_b200_ras_connect_conv)");
+    upload_peer_tables();
+    launch_conv_accumulate(ctx, P, rank, converged_all_local, conv(), conv_peer_dev_,
+                           num_converged_dev);
+}
+
 void Ras::conv_tree(int32_t converged_all_local)
 {
     upload_peer_tables();
@@ -739,6 +750,7 @@ void ras_run(std::vector<Ras *> &subs, const LoopOptions &o, LoopResult &res,
                 if (!(tol > 0.0 && iter_cond)) continue;
                 const int cal = (r->resnorm / r->resnorm0 <= tol) ? 1 : 0;
                 if (o.conv_tree) r->conv_tree(cal);
+                else if (o.conv_accumulate) r->conv_accumulate(cal);
                 else r->conv_forward(cal);
                 r->ctx.use();
                 SCHWZ_CUDA(cudaMemcpyAsync(&counts[i], r->num_converged_dev, sizeof(int32_t),

@@ -288,6 +288,7 @@ public:
     int32_t *err_word() const { return (int32_t *)(mailbox + mbox.err_off); }
     void conv_forward(int32_t converged_all_local);
     void conv_tree(int32_t converged_all_local);
+    void conv_accumulate(int32_t converged_all_local);
     int32_t exchange_mode = EXCHANGE_PUT_GATHERED;
 
 private:
@@ -327,7 +328,7 @@ struct LoopOptions {
     double tolerance = 1e-6;
     int32_t enable_onesided = 0, enable_global_check = 0, conv_decentralized = 0, iter_offset = 0;
     // one-sided only: ExchangeMode, and 1 = centralised tree instead of flag flooding
-    int32_t exchange_mode = 0, conv_tree = 0;
+    int32_t exchange_mode = 0, conv_tree = 0, conv_accumulate = 0;
     Comm *comm = nullptr;
 };
 struct LoopResult {

@@ -1149,6 +1149,34 @@ __global__ void conv_tree_kernel(int32_t P, int32_t me, int32_t converged_all_lo
     }
 }
 
+// Decentralised, accumulate variant (include/conv_tools.hpp:230-247,
+// --enable_decentralized_accumulate): while a subdomain is locally converged it adds 1 to word 0
+// of EVERY other subdomain's flags (MPI_Accumulate SUM -> a system-scope atomic add over NVLink)
+// and to its own; num_converged_procs = its word 0.  The counter keeps growing as long as
+// subdomains stay converged - the reference's semantics, kept.
+__global__ void conv_accumulate_kernel(int32_t P, int32_t me, int32_t converged_all_local,
+                                       int32_t *conv, int32_t *const *peer_conv,
+                                       int32_t *num_converged)
+{
+    const int t = threadIdx.x;
+    if (converged_all_local > 0)
+        for (int j = t; j < P; j += blockDim.x)
+            atomicAdd_system(j == me ? conv : peer_conv[j], 1);
+    __threadfence_system();
+    __syncthreads();
+    if (t == 0) *num_converged = ld_relaxed_sys_i32(conv + 0);
+}
+
+void launch_conv_accumulate(const Ctx &ctx, int32_t P, int32_t me, int32_t converged_all_local,
+                            int32_t *conv, int32_t *const *peer_conv, int32_t *num_converged)
+{
+    ctx.use();
+    conv_accumulate_kernel<<<1, 64, 0, ctx.stream>>>(P, me, converged_all_local, conv, peer_conv,
+                                                     num_converged);
+    SCHWZ_CUDA(cudaGetLastError());
+    count_launch();
+}
+
 void launch_conv_tree(const Ctx &ctx, int32_t P, int32_t me, int32_t converged_all_local,
                       int32_t *conv, int32_t *const *peer_conv, int32_t *num_converged)
 {

@@ -196,6 +196,17 @@ void Communicate<V, I, M>::clear(Settings &)
 // =============================================================================
 // Solve
 // =============================================================================
+// --write_perm_data (source/solve.cpp:434-453): one index per line, a blank line at the end
+static void write_perm_files(int rank, const std::vector<int32_t> &perm,
+                             const std::vector<int32_t> &inv_perm)
+{
+    for (int which = 0; which < 2; ++which) {
+        std::ofstream file((which == 0 ? "perm_" : "inv_perm_") + std::to_string(rank) + ".csv");
+        for (int32_t i : (which == 0 ? perm : inv_perm)) file << i << "\n";
+        file << std::endl;
+    }
+}
+
 template <typename V, typename I, typename M>
 void Solve<V, I, M>::setup_local_solver(
     const Settings &settings, Metadata<V, I> &metadata,
@@ -254,6 +265,7 @@ void Solve<V, I, M>::setup_local_solver(
         local_perm = gko::matrix::Permutation<I>::create(host, std::vector<I>(rowp.begin(), rowp.end()));
         local_inv_perm = gko::matrix::Permutation<I>::create(
             host, std::vector<I>(D.factor_perm.begin(), D.factor_perm.end()));
+        if (settings.write_perm_data) write_perm_files(metadata.my_rank, rowp, D.factor_perm);
         if (metadata.my_rank == 0)
             SAY(" Local direct solve with level-scheduled TRS");
     } else if (direct) {
@@ -291,6 +303,8 @@ void Solve<V, I, M>::setup_local_solver(
         local_perm = gko::matrix::Permutation<I>::create(
             host, std::vector<I>(D.factor_perm.begin(), D.factor_perm.end()));
         local_inv_perm = local_perm;
+        if (settings.write_perm_data)
+            write_perm_files(metadata.my_rank, D.factor_perm, D.factor_perm);
         if (metadata.my_rank == 0)
             SAY(" Local direct solve with level-scheduled TRS");
     } else if (solver == Settings::iterative_solver_ginkgo) {
@@ -319,7 +333,7 @@ void Solve<V, I, M>::setup_local_solver(
 }
 
 template <typename V, typename I, typename M>
-void Solve<V, I, M>::local_solve(const Settings &, Metadata<V, I> &metadata,
+void Solve<V, I, M>::local_solve(const Settings &settings, Metadata<V, I> &metadata,
                                  const std::shared_ptr<gko::matrix::Csr<V, I>> &,
                                  const std::shared_ptr<gko::matrix::Csr<V, I>> &,
                                  const std::shared_ptr<gko::matrix::Csr<V, I>> &,
@@ -330,6 +344,14 @@ void Solve<V, I, M>::local_solve(const Settings &, Metadata<V, I> &metadata,
                                  std::shared_ptr<gko::matrix::Dense<V>> &)
 {
     // source/solve.cpp:667-792 — asynchronous on the subdomain's stream
+    if (settings.local_solver == Settings::iterative_solver_ginkgo &&
+        settings.reset_local_crit_iter != -1 &&
+        (int)metadata.iter_count > settings.reset_local_crit_iter) {
+        // :721-741: past that outer iteration the local iteration cap becomes
+        // metadata.updated_max_iters (-1: the local size)
+        B200_CHECK(schwz_b200_ras_set_local_max_iters(solve_dev_->ras,
+                                                      (int32_t)metadata.updated_max_iters));
+    }
     B200_CHECK(schwz_b200_ras_local_solve(solve_dev_->ras));
     metadata.post_process_data.local_converged_iter_count.push_back(0);
     metadata.post_process_data.local_timestamp.push_back(MPI_Wtime() - metadata.init_mpi_wtime);
@@ -402,6 +424,8 @@ void Solve<V, I, M>::check_global_convergence(
             int32_t n = 0;
             if (settings.convergence_settings.enable_global_simple_tree)
                 B200_CHECK(schwz_b200_ras_conv_tree(solve_dev_->ras, converged_all_local));
+            else if (settings.convergence_settings.enable_accumulate)   // conv_tools.hpp:230-247
+                B200_CHECK(schwz_b200_ras_conv_accumulate(solve_dev_->ras, converged_all_local));
             else
                 B200_CHECK(schwz_b200_ras_conv_set_local(solve_dev_->ras, converged_all_local));
             B200_CHECK(schwz_b200_ras_conv_count(solve_dev_->ras, &n));

@@ -652,6 +652,9 @@ class Ras:
         pp = None if perm is None else _i32(perm)
         _chk(load().schwz_b200_ras_set_factors(self.h, _p(Lrp), _p(Lci), _p(Lv), _p(pp)))
 
+    def set_local_max_iters(self, cap):
+        _chk(load().schwz_b200_ras_set_local_max_iters(self.h, C.c_int32(cap)))
+
     def set_lu_factors(self, lu):
         """direct local solve Q U^-1 L^-1 P b with the factors of a HostLu"""
         _chk(load().schwz_b200_ras_set_lu_factors(self.h, lu.h, _p(lu.col_perm)))
@@ -681,6 +684,9 @@ class Ras:
 
     def conv_tree(self, converged_all_local):
         _chk(load().schwz_b200_ras_conv_tree(self.h, C.c_int32(int(converged_all_local))))
+
+    def conv_accumulate(self, converged_all_local):
+        _chk(load().schwz_b200_ras_conv_accumulate(self.h, C.c_int32(int(converged_all_local))))
 
     def conv_set_local(self, converged_all_local):
         _chk(load().schwz_b200_ras_conv_set_local(self.h, C.c_int32(int(converged_all_local))))
@@ -814,13 +820,15 @@ def connect_local(subs, setup):
 
 def ras_run(subs, num_subdomains, max_iters, tolerance=1e-6, enable_onesided=False,
             enable_global_check=True, conv_decentralized=False, iter_offset=False, comm=None,
-            history=False, exchange="put"):
+            history=False, exchange="put", enable_accumulate=False):
     """The outer loop of SchwarzBase::run (source/schwarz_base.cpp:387-452) over
     the subdomains of this process.  One-sided runs: conv_decentralized selects the flag
     flooding protocol (else the centralised tree), `exchange` one of EXCHANGE_MODES."""
     arr = (C.c_void_p * len(subs))(*[s.h for s in subs])
     o = LoopOptions(num_subdomains, max_iters, tolerance, int(enable_onesided),
-                    int(enable_global_check), int(conv_decentralized), int(iter_offset),
+                    int(enable_global_check),
+                    2 if (conv_decentralized and enable_accumulate) else int(conv_decentralized),
+                    int(iter_offset),
                     _exchange_mode(exchange), comm.h if comm is not None else None)
     res = LoopResult()
     hist = np.zeros((max_iters, len(subs))) if history else None

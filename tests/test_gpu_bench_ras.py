@@ -69,7 +69,11 @@ def test_regular2d_direct_and_oversubscription(tmp_path, orc):
     however many GPUs the box has."""
     out = _run(["--executor=cuda", "--explicit_laplacian", "--set_1d_laplacian_size=32",
                 "--partition=regular2d", "--local_solver=direct-ginkgo", "--enable_global_check",
-                "--num_iters=600", "--num_subdomains=16"], tmp_path)
+                "--num_iters=600", "--num_subdomains=16", "--write_perm_data"], tmp_path)
+    # --write_perm_data (source/solve.cpp:434-453): the factor ordering of every rank
+    perm = np.loadtxt(tmp_path / "perm_3.csv", dtype=np.int64)
+    assert sorted(perm) == list(range(len(perm))) and len(perm) >= 64
+    assert np.array_equal(perm, np.loadtxt(tmp_path / "inv_perm_3.csv", dtype=np.int64))
     pv = orc.partition_regular2d(32 * 32, 16)
     ob = orc.Problem(*orc.laplacian2d(32), 16, part=pv)
     ob.configure(max_iters=600, enable_global_check=True, local_solver="direct-ginkgo")

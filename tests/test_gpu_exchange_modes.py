@@ -124,6 +124,33 @@ def test_tree_protocol_step_by_step(sz):
     _close(ctxs, subs)
 
 
+def test_accumulate_protocol_step_by_step(sz):
+    """--enable_decentralized_accumulate (include/conv_tools.hpp:230-247): every call in which a
+    subdomain is locally converged adds 1 to word 0 of EVERY subdomain's flags; the count a
+    subdomain reports is its word 0.  Calls are serialised here (sync after each), so the
+    counts must equal the sequential model the oracle uses."""
+    P = 4
+    setup = sz.Setup(("laplacian2d", 12), P)
+    ctxs, subs = _build(sz, setup, P)
+    model = [0] * P                                    # word 0 of every subdomain
+    for flags in ([0, 0, 0, 0], [1, 0, 0, 0], [1, 0, 1, 0], [1, 1, 1, 1], [0, 0, 0, 1]):
+        for r, (s, f) in enumerate(zip(subs, flags)):
+            s.conv_accumulate(f)
+            if f:
+                model = [m + 1 for m in model]
+            assert s.conv_count() == model[r], (flags, r)   # conv_count synchronises
+    assert model == [9] * P                            # the counter steps over P: upstream's quirk
+    _close(ctxs, subs)
+    # through the loop (option plumbing only: whether the count ever EQUALS P depends on the
+    # order in which racing subdomains add and read, upstream as here)
+    setup = sz.Setup(("laplacian2d", 20), 2)
+    ctxs, subs = _build(sz, setup, 2)
+    out = sz.ras_run(subs, 2, 6, tolerance=1e-5, enable_onesided=True, conv_decentralized=True,
+                     enable_accumulate=True)
+    assert out["iters"] == 6 and not out["converged"]
+    _close(ctxs, subs)
+
+
 @pytest.mark.parametrize("mode", ["put", "get"])
 def test_mixed_precision_wire_format_rounds_to_float(sz, mode):
     """use_mixed_precision: gathered exchanges carry floats (half the NVLink bytes); the

@@ -313,3 +313,26 @@ def test_full_size_cfg2_properties(sz):
         s.close()
     for c in ctxs:
         c.close()
+
+
+def test_local_iteration_cap_can_be_reset_mid_run(sz):
+    """settings.reset_local_crit_iter / metadata.updated_max_iters (source/solve.cpp:721-741): past
+    a given outer iteration the local solver's iteration cap is replaced."""
+    P = 2
+    setup = sz.Setup(("laplacian2d", 200), P)          # 20 200 rows: the multi-kernel CG
+    ctxs = _fresh_ctxs(sz, P)
+    subs = _make(sz, ctxs, setup, P, local_max_iters=5)
+    _manual_step(subs, 0, P)
+    assert [s.last_local_iters() for s in subs] == [5, 5]
+    for s in subs:
+        s.set_local_max_iters(2)
+    _manual_step(subs, 1, P)
+    assert [s.last_local_iters() for s in subs] == [2, 2]
+    for s in subs:
+        s.set_local_max_iters(-1)                      # -1: the local size, i.e. to local_tol
+    _manual_step(subs, 2, P)
+    assert all(5 < s.last_local_iters() < s.local_size_x for s in subs)
+    for s in subs:
+        s.close()
+    for c in ctxs:
+        c.close()
