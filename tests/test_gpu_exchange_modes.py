@@ -139,7 +139,7 @@ def test_accumulate_protocol_step_by_step(sz):
             if f:
                 model = [m + 1 for m in model]
             assert s.conv_count() == model[r], (flags, r)   # conv_count synchronises
-    assert model == [9] * P                            # the counter steps over P: upstream's quirk
+    assert model == [8] * P                            # the counter steps over P: upstream's quirk
     _close(ctxs, subs)
     # through the loop (option plumbing only: whether the count ever EQUALS P depends on the
     # order in which racing subdomains add and read, upstream as here)
