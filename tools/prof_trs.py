@@ -1,0 +1,62 @@
+"""Timing of the level-scheduled triangular solves on the cfg5 factor (4096^2, regular2d 8x8:
+one 264 192-row subdomain, nested-dissection Cholesky, nnz(L) = 7.9 M): one L solve + one
+U = L^T solve, (a) alone on the GPU and (b) S solves side by side on S streams (the
+oversubscribed regime of cfg5: 8 subdomains per GPU on 8 GPUs, 64 on one).
+
+    python tools/prof_trs.py [S=16] [reps=20]
+"""
+import os
+import sys
+import time
+
+import numpy as np
+import scipy.sparse as sp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "schwarz-lib_b200"))
+import schwz_b200 as S
+
+nsub = int(sys.argv[1]) if len(sys.argv) > 1 else 16
+reps = int(sys.argv[2]) if len(sys.argv) > 2 else 20
+n, P = 4096, 64
+setup = S.Setup(("laplacian2d", n), P, part=S.partition_regular2d(n * n, P))
+rp, ci, v = setup.local_matrix(9)
+rows = len(rp) - 1
+perm = S.nd_ordering(rp, ci)
+Lrp, Lci, Lv = S.host_cholesky(rp, ci, v, perm)
+U = sp.csr_matrix((Lv, Lci, Lrp), shape=(rows, rows)).T.tocsr()
+U.sort_indices()
+Urp, Uci, Uv = U.indptr.astype(np.int32), U.indices.astype(np.int32), U.data
+ctxs = [S.Context(0) for _ in range(nsub)]
+plans = []
+b = np.random.default_rng(0).standard_normal(rows)
+for c in ctxs:
+    tl = S.Trs(c, Lrp, Lci, Lv, upper=False)
+    tu = S.Trs(c, Urp, Uci, Uv, upper=True)
+    plans.append((c, tl, tu, c.to_device(b), c.zeros(rows), c.zeros(rows)))
+c, tl, tu, db, dy, dz = plans[0]
+tl.solve(db, dy); tu.solve(dy, dz); c.sync()
+z = c.to_host(dz, rows)
+Lm = sp.csr_matrix((Lv, Lci, Lrp), shape=(rows, rows))
+print("residual |L L^T z - b| / |b| = %.2e, levels %d" % (np.linalg.norm(Lm @ (Lm.T @ z) - b) / np.linalg.norm(b), tl.levels()))
+# (a) alone
+c.timer_start()
+for _ in range(reps):
+    tl.solve(db, dy); tu.solve(dy, dz)
+ms = c.timer_stop() / reps
+byts = 2 * (12 * int(Lrp[-1]) + 20 * rows)
+print("alone: L + U solve %.1f us, %.1f GB/s algorithmic" % (ms * 1e3, byts / ms / 1e6))
+# (b) nsub side by side
+for (c, tl, tu, db, dy, dz) in plans:
+    tl.solve(db, dy); tu.solve(dy, dz)
+for (c, *_rest) in plans:
+    c.sync()
+t0 = time.perf_counter()
+for _ in range(reps):
+    for (c, tl, tu, db, dy, dz) in plans:
+        tl.solve(db, dy); tu.solve(dy, dz)
+for (c, *_rest) in plans:
+    c.sync()
+dt = (time.perf_counter() - t0) / reps
+print("%d side by side: %.1f us per (L + U) pair, %.2f ms per sweep over all, %.1f GB/s aggregate"
+      % (nsub, dt / nsub * 1e6, dt * 1e3, nsub * byts / dt / 1e9))
