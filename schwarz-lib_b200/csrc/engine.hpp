@@ -145,7 +145,7 @@ public:
     // stop: optional device flag, the launches are no-ops when it is set
     void solve(const double *b, double *x, const int32_t *stop = nullptr);
     int32_t num_levels() const { return num_levels_; }
-    int32_t num_launches() const { return (int32_t)segments_.size(); }
+    int32_t num_launches() const { return (int32_t)segments_.size() + num_blocks_; }
     int64_t nnz() const { return nnz_; }
 
 private:
@@ -153,10 +153,11 @@ private:
     int32_t n_, num_levels_ = 0;
     int64_t nnz_ = 0;
     bool upper_;
-    int32_t *rp_ = nullptr, *ci_ = nullptr, *order_ = nullptr;   // rows sorted by level
+    // the factor in level order, off-diagonal entries only: position i = row order_[i], entries
+    // [rp_[i], rp_[i+1]), reciprocal diagonal inv_diag_[i]
+    int32_t *rp_ = nullptr, *ci_ = nullptr, *order_ = nullptr;
     double *v_ = nullptr, *inv_diag_ = nullptr;
-    std::vector<int32_t> level_ptr_;   // host: level l = order[level_ptr[l] .. level_ptr[l+1])
-    int32_t *level_ptr_dev_ = nullptr;
+    std::vector<int32_t> level_ptr_;   // host: level l = positions [level_ptr[l], level_ptr[l+1])
     // Runs of consecutive small levels (the dense top of a nested-dissection factor: 3 % of
     // the rows, 60 % of the non-zeros, 90 % of the levels) are solved block-wise: a block =
     // up to kTrsBlock consecutive rows of the level order, x_K = Dinv_K (b_K - Lout_K x),
@@ -165,6 +166,8 @@ private:
         int32_t kind;      // 0: one wide level, 1: one block
         int32_t a, b;      // kind 0: level index, unused; kind 1: first position, rows
         int64_t dinv_off;  // kind 1: offset of the dense inverse (column-major, ld = rows)
+        int32_t mode;      // kind 0: 1 = one thread per row (short rows); kind 1: 2 = a CTA per
+                           // row for the part outside the block (long rows); 0 = a warp per row
     };
     std::vector<Segment> segments_;
     int32_t *chain_rp_ = nullptr, *chain_ci_ = nullptr;   // outside entries, indexed by position

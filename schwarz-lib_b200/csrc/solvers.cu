@@ -514,41 +514,65 @@ void GmresSolver::result(int32_t *iters, double *resnorm, double *resnorm0)
 constexpr int kTrsWarps = kBlock / 32;
 constexpr int kTrsSmallLevel = 8 * kTrsWarps;   // rows a single CTA sweeps per level
 
-__device__ __forceinline__ void trs_row(int32_t row, const int32_t *__restrict__ rp,
+// The factor is stored in LEVEL ORDER, off-diagonal entries only: position i of the level order
+// is row order[i] with entries [prp[i], prp[i+1]) and reciprocal diagonal pinv[i].  That takes
+// two dependent loads (level bounds, order[i] -> rp[row]) out of the critical path of every
+// launch - these solves are bound by the memory latency of a short dependent chain per level,
+// not by bandwidth.
+__device__ __forceinline__ void trs_row(int32_t i, const int32_t *__restrict__ order,
+                                        const int32_t *__restrict__ prp,
                                         const int32_t *__restrict__ ci,
                                         const double *__restrict__ v,
-                                        const double *__restrict__ inv_diag,
+                                        const double *__restrict__ pinv,
                                         const double *__restrict__ b, volatile double *x, int lane)
 {
+    const int32_t row = order[i];
+    const int32_t k1 = prp[i + 1];
+    const double rhs = b[row], d = pinv[i];   // independent of the gathers below
+    // 4 independent (index, value, x) gathers per lane in flight
     double s = 0.0;
-    for (int32_t k = rp[row] + lane; k < rp[row + 1]; k += 32) {
-        const int32_t c = ci[k];
-        if (c != row) s += v[k] * x[c];
+    for (int32_t k = prp[i] + lane; k < k1; k += 128) {
+        double t[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int32_t kk = k + 32 * u;
+            if (kk < k1) t[u] = v[kk] * x[ci[kk]];
+        }
+        s += (t[0] + t[1]) + (t[2] + t[3]);
     }
     s = warp_sum(s);
-    if (lane == 0) x[row] = (b[row] - s) * inv_diag[row];
+    if (lane == 0) x[row] = (rhs - s) * d;
 }
 
-// one launch = levels [l0, l1); grid > 1 only when l1 == l0 + 1
+// one launch = positions [a, e) of the level order (one level), a warp per row
 __global__ void __launch_bounds__(kBlock)
-    trs_levels_kernel(int32_t l0, int32_t l1, const int32_t *__restrict__ level_ptr,
-                      const int32_t *__restrict__ order, const int32_t *__restrict__ rp,
-                      const int32_t *__restrict__ ci, const double *__restrict__ v,
-                      const double *__restrict__ inv_diag, const double *__restrict__ b,
-                      double *x, const int32_t *stop)
+    trs_levels_kernel(int32_t a, int32_t e, const int32_t *__restrict__ order,
+                      const int32_t *__restrict__ prp, const int32_t *__restrict__ ci,
+                      const double *__restrict__ v, const double *__restrict__ pinv,
+                      const double *__restrict__ b, double *x, const int32_t *stop)
 {
     if (stop != nullptr && *stop != 0) return;
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * kBlock + threadIdx.x) >> 5;
     const int nwarps = (gridDim.x * kBlock) >> 5;
-    for (int32_t l = l0; l < l1; ++l) {
-        const int32_t a = level_ptr[l], e = level_ptr[l + 1];
-        for (int32_t i = a + warp; i < e; i += nwarps)
-            trs_row(order[i], rp, ci, v, inv_diag, b, x, lane);
-        if (l + 1 < l1) {
-            __threadfence_block();
-            __syncthreads();
-        }
+    for (int32_t i = a + warp; i < e; i += nwarps) trs_row(i, order, prp, ci, v, pinv, b, x, lane);
+}
+
+// A wide level of SHORT rows (the leaves of a nested-dissection factor: 10^5 rows of 0..8
+// entries): one thread per row; a warp per row would idle 24+ of its lanes and walk a dozen
+// rows one after the other.
+__global__ void __launch_bounds__(kBlock)
+    trs_level_thread_kernel(int32_t a, int32_t e, const int32_t *__restrict__ order,
+                            const int32_t *__restrict__ prp, const int32_t *__restrict__ ci,
+                            const double *__restrict__ v, const double *__restrict__ pinv,
+                            const double *__restrict__ b, double *x, const int32_t *stop)
+{
+    if (stop != nullptr && *stop != 0) return;
+    for (int32_t i = a + blockIdx.x * kBlock + threadIdx.x; i < e; i += gridDim.x * kBlock) {
+        const int32_t row = order[i];
+        double s = 0.0;
+        for (int32_t k = prp[i]; k < prp[i + 1]; ++k) s += v[k] * x[ci[k]];
+        x[row] = (b[row] - s) * pinv[i];
     }
 }
 
@@ -557,50 +581,81 @@ __global__ void __launch_bounds__(kBlock)
 // by the block's explicit inverse: x_K = Dinv_K t.
 constexpr int kTrsBlock = 128;
 
+// phase A: t_i = b_i - (entries of row i outside the block) . x
 __global__ void __launch_bounds__(kBlock)
-    trs_block_kernel(int32_t pos0, int32_t nrows, const int32_t *__restrict__ order,
-                     const int32_t *__restrict__ crp, const int32_t *__restrict__ cci,
-                     const double *__restrict__ cv, const double *__restrict__ dinv,
-                     const double *__restrict__ b, double *x, double *t_scratch,
-                     unsigned int *ticket, const int32_t *stop)
+    trs_block_a_kernel(int32_t pos0, int32_t nrows, const int32_t *__restrict__ order,
+                       const int32_t *__restrict__ crp, const int32_t *__restrict__ cci,
+                       const double *__restrict__ cv, const double *__restrict__ b,
+                       const double *__restrict__ x, double *__restrict__ t_scratch,
+                       const int32_t *stop, int cta_per_row)
 {
-    __shared__ double s_t[kTrsBlock];
-    __shared__ bool s_last;
     if (stop != nullptr && *stop != 0) return;
     const int lane = threadIdx.x & 31;
+    if (cta_per_row) {
+        // long rows (the dense separator triangles: hundreds to thousands of outside entries
+        // per row): the whole CTA strides over one row, 4 independent gathers per thread in
+        // flight; with a warp per row only 128 warps would carry the block's 1-2 MB
+        __shared__ double s_red[kBlock / 32];
+        for (int32_t i = blockIdx.x; i < nrows; i += gridDim.x) {
+            const int32_t p = pos0 + i;
+            const int32_t k0 = crp[p], k1 = crp[p + 1];
+            const double rhs = b[order[p]];
+            double s = 0.0;
+            for (int32_t k = k0 + threadIdx.x; k < k1; k += 4 * kBlock) {
+                double t0 = cv[k] * x[cci[k]], t1 = 0.0, t2 = 0.0, t3 = 0.0;
+                if (k + kBlock < k1) t1 = cv[k + kBlock] * x[cci[k + kBlock]];
+                if (k + 2 * kBlock < k1) t2 = cv[k + 2 * kBlock] * x[cci[k + 2 * kBlock]];
+                if (k + 3 * kBlock < k1) t3 = cv[k + 3 * kBlock] * x[cci[k + 3 * kBlock]];
+                s += (t0 + t1) + (t2 + t3);
+            }
+            s = block_sum(s, s_red);
+            if (threadIdx.x == 0) t_scratch[i] = rhs - s;
+        }
+        return;
+    }
     const int warp = (blockIdx.x * kBlock + threadIdx.x) >> 5;
     const int nwarps = (gridDim.x * kBlock) >> 5;
     for (int32_t i = warp; i < nrows; i += nwarps) {
         const int32_t p = pos0 + i;
+        const double rhs = b[order[p]];
         double s = 0.0;
         for (int32_t k = crp[p] + lane; k < crp[p + 1]; k += 32) s += cv[k] * x[cci[k]];
         s = warp_sum(s);
-        if (lane == 0) t_scratch[i] = b[order[p]] - s;
+        if (lane == 0) t_scratch[i] = rhs - s;
     }
-    if (gridDim.x > 1) {
-        __threadfence();
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            const unsigned int tk = atomicAdd(ticket, 1u);
-            s_last = (tk == gridDim.x - 1);
-            if (s_last) *ticket = 0u;
-        }
-        __syncthreads();
-        if (!s_last) return;
-        __threadfence();
-    } else {
-        __syncthreads();
-    }
-    for (int i = threadIdx.x; i < nrows; i += kBlock) s_t[i] = __ldcg(t_scratch + i);
+}
+
+// phase B, its own launch (the kernel boundary replaces a fence + ticket + reload in the last
+// CTA): x_K = Dinv t.  Dinv row-major (lower triangle); a warp per row with the lanes across
+// the columns (coalesced), four rows of a warp in flight at once; 4 CTAs cover 128 rows.
+__global__ void __launch_bounds__(kBlock)
+    trs_block_b_kernel(int32_t pos0, int32_t nrows, const int32_t *__restrict__ order,
+                       const double *__restrict__ dinv, const double *__restrict__ t_scratch,
+                       double *__restrict__ x, const int32_t *stop)
+{
+    __shared__ double s_t[kTrsBlock];
+    if (stop != nullptr && *stop != 0) return;
+    const int lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < nrows; i += kBlock) s_t[i] = t_scratch[i];
     __syncthreads();
-    // two threads per row split the columns (even / odd); Dinv is column-major so that the
-    // threads of a warp read consecutive addresses
-    const int row = threadIdx.x >> 1, half = threadIdx.x & 1;
-    double acc = 0.0;
-    if (row < nrows)
-        for (int j = half; j <= row; j += 2) acc += dinv[(size_t)j * nrows + row] * s_t[j];
-    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-    if (row < nrows && half == 0) x[order[pos0 + row]] = acc;
+    const int w = blockIdx.x * (kBlock / 32) + (threadIdx.x >> 5);
+    const int r0 = 4 * w;
+    if (r0 >= nrows) return;
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+    for (int jj = 0; jj < kTrsBlock / 32; ++jj) {
+        const int j = lane + 32 * jj;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int r = r0 + u;
+            if (r < nrows && j <= r) acc[u] += dinv[(size_t)r * nrows + j] * s_t[j];
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const double a = warp_sum(acc[u]);
+        if (lane == 0 && r0 + u < nrows) x[order[pos0 + r0 + u]] = a;
+    }
 }
 
 TrsPlan::TrsPlan(const Ctx &ctx, int32_t n, const int32_t *rp, const int32_t *ci,
@@ -629,15 +684,31 @@ TrsPlan::TrsPlan(const Ctx &ctx, int32_t n, const int32_t *rp, const int32_t *ci
     for (int32_t l = 0; l < num_levels_; ++l) level_ptr_[l + 1] += level_ptr_[l];
     std::vector<int32_t> order(n), cur(level_ptr_.begin(), level_ptr_.end() - 1);
     for (int32_t i = 0; i < n; ++i) order[cur[level[i]]++] = i;
-    rp_ = ctx.upload(rp, (size_t)n + 1);
-    ci_ = ctx.upload(ci, (size_t)nnz_);
-    v_ = ctx.upload(v, (size_t)nnz_);
+    {
+        // level-ordered copy of the factor, off-diagonal entries only
+        std::vector<int32_t> prp((size_t)n + 1, 0), pci;
+        std::vector<double> pv, pinv((size_t)n);
+        pci.reserve((size_t)nnz_);
+        pv.reserve((size_t)nnz_);
+        for (int32_t i = 0; i < n; ++i) {
+            const int32_t row = order[i];
+            for (int32_t k = rp[row]; k < rp[row + 1]; ++k)
+                if (ci[k] != row && (upper ? ci[k] > row : ci[k] < row)) {
+                    pci.push_back(ci[k]);
+                    pv.push_back(v[k]);
+                }
+            prp[i + 1] = (int32_t)pci.size();
+            pinv[i] = inv_diag[row];
+        }
+        rp_ = ctx.upload(prp.data(), prp.size());
+        ci_ = ctx.upload(pci.data(), pci.size());
+        v_ = ctx.upload(pv.data(), pv.size());
+        inv_diag_ = ctx.upload(pinv.data(), pinv.size());
+    }
     order_ = ctx.upload(order.data(), (size_t)n);
-    inv_diag_ = ctx.upload(inv_diag.data(), (size_t)n);
-    level_ptr_dev_ = ctx.upload(level_ptr_.data(), level_ptr_.size());
 
     // ---- segments: wide levels one by one, runs of small levels cut into blocks ----------
-    static_assert(2 * kTrsBlock <= kBlock, "two threads per block row in trs_block_kernel");
+    static_assert(kTrsBlock % 32 == 0 && kTrsBlock <= kBlock, "trs_block_kernel stages t in one pass");
     std::vector<int32_t> crp(1, 0), cci, pos_in_block((size_t)n, -1);
     std::vector<double> cv, dinv;
     std::vector<int32_t> chain_first;   // position of every chain row -> index into crp
@@ -647,7 +718,11 @@ TrsPlan::TrsPlan(const Ctx &ctx, int32_t n, const int32_t *rp, const int32_t *ci
     while (l < num_levels_) {
         const int32_t rows = level_ptr_[l + 1] - level_ptr_[l];
         if (rows > kTrsSmallLevel) {
-            segments_.push_back({0, l, 0, 0});
+            // mode 1: more rows than the grid has warps, and short ones -> one thread per row
+            int64_t lnnz = 0;
+            for (int32_t i = level_ptr_[l]; i < level_ptr_[l + 1]; ++i)
+                lnnz += rp[order[i] + 1] - rp[order[i]];
+            segments_.push_back({0, l, 0, 0, (rows > 8192 && lnnz <= 8 * (int64_t)rows) ? 1 : 0});
             ++l;
             continue;
         }
@@ -676,7 +751,7 @@ TrsPlan::TrsPlan(const Ctx &ctx, int32_t n, const int32_t *rp, const int32_t *ci
                 crp.push_back((int32_t)cci.size());
             }
             // explicit inverse of the lower-triangular block (row-major D, forward substitution
-            // on the identity), stored column-major with ld = nb
+            // on the identity), kept row-major with ld = nb for the device
             Dinv.assign((size_t)nb * nb, 0.0);
             for (int32_t j = 0; j < nb; ++j) {
                 for (int32_t i = j; i < nb; ++i) {
@@ -685,8 +760,11 @@ TrsPlan::TrsPlan(const Ctx &ctx, int32_t n, const int32_t *rp, const int32_t *ci
                     Dinv[(size_t)j * nb + i] = sacc / D[(size_t)i * nb + i];
                 }
             }
-            segments_.push_back({1, p0, nb, (int64_t)dinv.size()});
-            dinv.insert(dinv.end(), Dinv.begin(), Dinv.end());
+            // mode 2: long rows -> a CTA per row for the outside part
+            const int64_t outside = (int64_t)cci.size() - crp[crp.size() - 1 - nb];
+            segments_.push_back({1, p0, nb, (int64_t)dinv.size(), outside >= 128 * (int64_t)nb ? 2 : 0});
+            for (int32_t i = 0; i < nb; ++i)      // Dinv above is column-major: transpose
+                for (int32_t j = 0; j < nb; ++j) dinv.push_back(Dinv[(size_t)j * nb + i]);
             for (int32_t i = 0; i < nb; ++i) pos_in_block[order[p0 + i]] = -1;
             ++num_blocks_;
         }
@@ -726,7 +804,6 @@ TrsPlan::~TrsPlan()
     ctx_.release(v_);
     ctx_.release(order_);
     ctx_.release(inv_diag_);
-    ctx_.release(level_ptr_dev_);
     ctx_.release(chain_rp_);
     ctx_.release(chain_ci_);
     ctx_.release(chain_v_);
@@ -756,15 +833,24 @@ void TrsPlan::solve(const double *b, double *x, const int32_t *stop)
         if (sg.kind == 0) {
             const int32_t l = sg.a;
             const int32_t rows = level_ptr_[l + 1] - level_ptr_[l];
+            if (sg.mode == 1) {
+                const int grid = std::min((rows + kBlock - 1) / kBlock, kVecGrid);
+                trs_level_thread_kernel<<<grid, kBlock, 0, ctx_.stream>>>(
+                    level_ptr_[l], level_ptr_[l + 1], order_, rp_, ci_, v_, inv_diag_, b, x, stop);
+                continue;
+            }
             const int grid = std::min((rows + kTrsWarps - 1) / kTrsWarps, kVecGrid);
-            trs_levels_kernel<<<grid, kBlock, 0, ctx_.stream>>>(l, l + 1, level_ptr_dev_, order_,
-                                                                rp_, ci_, v_, inv_diag_, b, x,
-                                                                stop);
+            trs_levels_kernel<<<grid, kBlock, 0, ctx_.stream>>>(level_ptr_[l], level_ptr_[l + 1],
+                                                                order_, rp_, ci_, v_, inv_diag_,
+                                                                b, x, stop);
         } else {
-            const int grid = std::max(1, (sg.b + kTrsWarps - 1) / kTrsWarps);
-            trs_block_kernel<<<grid, kBlock, 0, ctx_.stream>>>(
-                sg.a, sg.b, order_, chain_rp_, chain_ci_, chain_v_, dinv_ + sg.dinv_off, b, x,
-                block_t_, ctx_.tickets + 6, stop);
+            const int grid = sg.mode == 2 ? sg.b : std::max(1, (sg.b + kTrsWarps - 1) / kTrsWarps);
+            trs_block_a_kernel<<<grid, kBlock, 0, ctx_.stream>>>(
+                sg.a, sg.b, order_, chain_rp_, chain_ci_, chain_v_, b, x, block_t_, stop,
+                sg.mode == 2 ? 1 : 0);
+            trs_block_b_kernel<<<(sg.b + 4 * kTrsWarps - 1) / (4 * kTrsWarps), kBlock, 0,
+                                 ctx_.stream>>>(sg.a, sg.b, order_, dinv_ + sg.dinv_off, block_t_,
+                                                x, stop);
         }
     }
     SCHWZ_CUDA(cudaStreamEndCapture(ctx_.stream, &graph));

@@ -60,3 +60,28 @@ for (c, *_rest) in plans:
 dt = (time.perf_counter() - t0) / reps
 print("%d side by side: %.1f us per (L + U) pair, %.2f ms per sweep over all, %.1f GB/s aggregate"
       % (nsub, dt / nsub * 1e6, dt * 1e3, nsub * byts / dt / 1e9))
+
+# (c) the same with one host thread per subdomain (what bench_ras does: ranks are threads), to
+# separate the host's graph-launch cost from what the GPU can overlap
+from concurrent.futures import ThreadPoolExecutor
+
+
+def worker(pl):
+    c, tl, tu, db, dy, dz = pl
+    for _ in range(reps):
+        tl.solve(db, dy); tu.solve(dy, dz)
+    c.sync()
+
+
+t0 = time.perf_counter()
+with ThreadPoolExecutor(nsub) as ex:
+    list(ex.map(worker, plans))
+dt = (time.perf_counter() - t0) / reps
+print("%d side by side, one host thread each: %.1f us per (L + U) pair, %.2f ms per sweep, %.1f GB/s aggregate"
+      % (nsub, dt / nsub * 1e6, dt * 1e3, nsub * byts / dt / 1e9))
+t0 = time.perf_counter()
+for _ in range(reps):
+    tl.solve(db, dy); tu.solve(dy, dz)
+host = (time.perf_counter() - t0) / reps
+c.sync()
+print("host time to enqueue one (L + U) pair: %.1f us (%d levels)" % (host * 1e6, tl.levels()))
