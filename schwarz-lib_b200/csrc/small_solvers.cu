@@ -9,6 +9,7 @@
 // solvers.cu (Ginkgo semantics).  Rows are summed
 // sequentially in stored order, as everywhere else.
 #include <algorithm>
+#include <cstdlib>
 
 #include "engine.hpp"
 
@@ -131,8 +132,19 @@ __global__ void __launch_bounds__(kSmallThreads, 1)
 
 bool cg_small_fits(int64_t n) { return n > 0 && (4 * n + kSmallBuf) * 8 <= 220 * 1024; }
 
-// threads by size: few warps make the barriers cheap, many warps hide the row gathers
-static int small_threads(int64_t n) { return n <= 1024 ? 128 : n <= 4096 ? 256 : 1024; }
+// threads by size: few warps make the barriers cheap, many warps hide the gathers
+static int small_threads(int64_t n)
+{
+    static int forced = -1;
+    if (forced < 0) {
+        const char *e = std::getenv("SCHWZ_B200_SMALL_THREADS");   // A/B aid: 128, 256 or 1024
+        forced = e ? std::atoi(e) : 0;
+    }
+    if (forced == 128 || forced == 256 || forced == 1024) return forced;
+    // measured (tools/prof_small.py): 457 rows 10.8 / 14.5 / 14.5 us per GMRES(30) step with
+    // 256 / 128 / 1024 threads; from 827 rows up 1024 threads win (18.1 vs 18.3 vs 19.8 us)
+    return n <= 640 ? 256 : 1024;
+}
 
 void launch_cg_small(const Ctx &ctx, const DeviceCsr &A, const double *b, double *x,
                      int32_t max_iters, double tol, CgScalars *out, const int32_t *outer_stop)
