@@ -503,16 +503,20 @@ void GmresSolver::result(int32_t *iters, double *resnorm, double *resnorm0)
 // Level-scheduled sparse triangular solve (replaces gko::solver::LowerTrs /
 // UpperTrs, i.e. cuSPARSE csrsm2 with the level policy on the reference's CUDA
 // path).  Host analysis assigns level(i) = 1 + max level of the rows that row
-// i depends on; rows are processed level by level, one warp per row, lanes
-// striding over the row's entries (coalesced), fixed-shape shuffle reduction.
-// Small consecutive levels are merged into one single-CTA launch that walks
-// them with __syncthreads() between levels, which is what bounds the launch
-// count on nested-dissection factors (a long chain of tiny levels at the top
-// of the elimination tree).
+// i depends on; a wide level is one launch (a warp per row, lanes striding over
+// the row's entries, fixed-shape shuffle reduction; one thread per row for the
+// huge levels of 1..8-entry rows at the leaves), all launches of a solve in one
+// CUDA graph.  Runs of small levels - the dense separator triangles at the top
+// of a nested-dissection factor, a chain of 1..8-row levels holding most of
+// the non-zeros - are cut into blocks of <= 128 consecutive rows and solved as
+// x_K = Dinv_K (b_K - L[K, outside] x) with the explicit inverse of the block's
+// own triangle: two launches per block instead of one per level.
+// The solves are bound by the memory latency of a short dependent chain per
+// launch, not by bandwidth (tools/prof_trs.py).
 // Algorithmic bytes: 12*nnz + 20*rows.
 // =============================================================================
 constexpr int kTrsWarps = kBlock / 32;
-constexpr int kTrsSmallLevel = 8 * kTrsWarps;   // rows a single CTA sweeps per level
+constexpr int kTrsSmallLevel = 8 * kTrsWarps;   // levels of at most this many rows go into blocks
 
 // The factor is stored in LEVEL ORDER, off-diagonal entries only: position i of the level order
 // is row order[i] with entries [prp[i], prp[i+1]) and reciprocal diagonal pinv[i].  That takes
