@@ -336,3 +336,32 @@ def test_local_iteration_cap_can_be_reset_mid_run(sz):
         s.close()
     for c in ctxs:
         c.close()
+
+
+@pytest.mark.parametrize("n,seed,P,spd", [(400, 3, 5, True), (260, 6, 6, False)])
+def test_random_matrix_iterates_match_oracle(sz, orc, n, seed, P, spd):
+    """Random sparse matrices (symmetric pattern, ragged rows, hub rows), METIS partition - the
+    inputs on which tests/test_ref_pinning_random.py pins the oracle to the reference run: the
+    CUDA path reproduces the oracle's iterates within 1e-10 at every outer iteration."""
+    from test_ref_pinning_random import random_matrix
+    mat = random_matrix(n, seed, spd)
+    part = sz.partition_metis(mat[0], mat[1], P)
+    kw = {} if spd else dict(non_symmetric=True, restart_iter=20)
+    ob = orc.Problem(*mat, P, part=part)
+    ob.configure(tolerance=1e-10, local_tol=1e-12, max_iters=100, enable_global_check=True, **kw)
+    setup = sz.Setup(mat, P, part=part)
+    ctxs = _fresh_ctxs(sz, P)
+    subs = _make(sz, ctxs, setup, P, local_tol=1e-12, **kw)
+    for it in range(10):
+        norms = _manual_step(subs, it, P)
+        ob.step()
+        for r in range(P):
+            assert norms[r] == pytest.approx(ob.status(r)["resnorm"], rel=1e-9, abs=1e-13)
+            l2g = setup.l2g(r)
+            xo = ob.x(r)[l2g]
+            xg = _gpu_x_global(subs[r], setup, r, n)[l2g]
+            assert np.linalg.norm(xg - xo) <= TOL_ITERATE * max(np.linalg.norm(xo), 1e-300), (it, r)
+    for s in subs:
+        s.close()
+    for c in ctxs:
+        c.close()
