@@ -146,8 +146,13 @@ int main(int argc, char *argv[])
             P = n > 0 ? n : 1;
         }
         schwz_mpi::RankGroup::instance().run(P, [](int) {
-            BenchRas<double, int> laplace_problem_2d;
-            laplace_problem_2d.run();
+            if (FLAGS_index_bits == 64) {   // the reference instantiates (double, int64) too
+                BenchRas<double, gko::int64> laplace_problem_2d;
+                laplace_problem_2d.run();
+            } else {
+                BenchRas<double, int> laplace_problem_2d;
+                laplace_problem_2d.run();
+            }
         });
         MPI_Finalize();
     } catch (std::exception &exc) {

@@ -21,6 +21,40 @@
 
 #include "schwz_classes.hpp"
 
+namespace {
+// The C ABI speaks int32.  With IndexType = int32 these views are the caller's own pointers;
+// with IndexType = int64 (the reference instantiates both, include/settings.hpp:533-537) values
+// are narrowed on the way in (range-checked) and widened on the way out.
+template <typename I>
+struct Out32 {   // a buffer the library fills
+    Out32(I *p, size_t n) : dst_(p), tmp_(std::is_same<I, int32_t>::value ? 0 : n) {}
+    operator int32_t *() { return std::is_same<I, int32_t>::value ? (int32_t *)(void *)dst_ : tmp_.data(); }
+    ~Out32()
+    {
+        for (size_t k = 0; k < tmp_.size(); ++k) dst_[k] = (I)tmp_[k];
+    }
+    I *dst_;
+    std::vector<int32_t> tmp_;
+};
+template <typename I>
+struct In32 {    // a buffer the library reads
+    In32(const I *p, size_t n) : src_(p), tmp_(std::is_same<I, int32_t>::value ? 0 : n)
+    {
+        for (size_t k = 0; k < tmp_.size(); ++k) {
+            if (p[k] > (I)2147483647 || p[k] < (I)-2147483647 - 1)
+                throw std::runtime_error("index does not fit the 32-bit device index type");
+            tmp_[k] = (int32_t)p[k];
+        }
+    }
+    operator const int32_t *() const
+    {
+        return std::is_same<I, int32_t>::value ? (const int32_t *)(const void *)src_ : tmp_.data();
+    }
+    const I *src_;
+    std::vector<int32_t> tmp_;
+};
+}  // namespace
+
 #define B200_CHECK(expr) ::schwz::b200::check((expr), __FILE__, __LINE__)
 
 namespace schwz {
@@ -107,11 +141,13 @@ void Initialize<V, I>::setup_global_matrix(const std::string &filename,
         if (N <= kMaterializeLimit) {
             global_matrix->allocate();
             if (three_d)
-                schwz_b200_laplacian3d((int32_t)n, global_matrix->get_row_ptrs(),
-                                       global_matrix->get_col_idxs(), global_matrix->get_values());
+                schwz_b200_laplacian3d((int32_t)n, Out32<I>(global_matrix->get_row_ptrs(), N + 1),
+                                       Out32<I>(global_matrix->get_col_idxs(), nnz),
+                                       global_matrix->get_values());
             else
-                schwz_b200_laplacian2d((int32_t)n, global_matrix->get_row_ptrs(),
-                                       global_matrix->get_col_idxs(), global_matrix->get_values());
+                schwz_b200_laplacian2d((int32_t)n, Out32<I>(global_matrix->get_row_ptrs(), N + 1),
+                                       Out32<I>(global_matrix->get_col_idxs(), nnz),
+                                       global_matrix->get_values());
         }
     } else {
         std::cerr << " Need to provide a matrix or enable the default laplacian matrix." << std::endl;
@@ -134,9 +170,11 @@ void Initialize<V, I>::partition(const Settings &settings, const Metadata<V, I> 
         if (!global_matrix->has_arrays())
             throw std::runtime_error("METIS partitioning needs the stored global matrix");
         B200_CHECK(schwz_b200_partition_metis(
-            (int32_t)metadata.global_size, global_matrix->get_const_row_ptrs(),
-            global_matrix->get_const_col_idxs(), (int32_t)metadata.num_subdomains,
-            settings.metis_objtype.c_str(), partition_indices.data()));
+            (int32_t)metadata.global_size,
+            In32<I>(global_matrix->get_const_row_ptrs(), metadata.global_size + 1),
+            In32<I>(global_matrix->get_const_col_idxs(), global_matrix->get_num_stored_elements()),
+            (int32_t)metadata.num_subdomains, settings.metis_objtype.c_str(),
+            partition_indices.data()));
     } else if (kind == Settings::partition_regular) {
         SAY(" Regular 1D partition");
     } else if (kind == Settings::partition_regular2d) {
@@ -778,9 +816,10 @@ void SolverRAS<V, I, M>::setup_local_matrices(
         const uint32_t *part = permute ? partition_indices.data() : nullptr;
         if (global_matrix->has_arrays()) {
             B200_CHECK(schwz_b200_setup_create(
-                0, 0, (int32_t)metadata.global_size, global_matrix->get_const_row_ptrs(),
-                global_matrix->get_const_col_idxs(), global_matrix->get_const_values(), P,
-                permute ? 1 : 0, part, settings.overlap, &s));
+                0, 0, (int32_t)metadata.global_size,
+                In32<I>(global_matrix->get_const_row_ptrs(), metadata.global_size + 1),
+                In32<I>(global_matrix->get_const_col_idxs(), global_matrix->get_num_stored_elements()),
+                global_matrix->get_const_values(), P, permute ? 1 : 0, part, settings.overlap, &s));
         } else {
             B200_CHECK(schwz_b200_setup_create(settings.laplacian_dim == 3 ? 2 : 1,
                                                (int32_t)metadata.oned_laplacian_size,
@@ -796,7 +835,8 @@ void SolverRAS<V, I, M>::setup_local_matrices(
     auto host = settings.executor->get_master();
     for (int turn = 0; turn < P; ++turn) {
         if (turn == me) {
-            B200_CHECK(schwz_b200_setup_first_row(D.setup, metadata.first_row->get_data()));
+            B200_CHECK(schwz_b200_setup_first_row(D.setup,
+                                                  Out32<I>(metadata.first_row->get_data(), P + 1)));
             int64_t sz[8];
             B200_CHECK(schwz_b200_setup_sizes(D.setup, me, sz));
             metadata.local_size = sz[0];
@@ -804,27 +844,31 @@ void SolverRAS<V, I, M>::setup_local_matrices(
             metadata.local_size_o = metadata.global_size;
             metadata.overlap_size = sz[2];
             metadata.local_to_global = std::make_shared<gko::Array<I>>(host, sz[1] + sz[5]);
-            B200_CHECK(schwz_b200_setup_l2g(D.setup, me, metadata.local_to_global->get_data()));
+            B200_CHECK(schwz_b200_setup_l2g(
+                D.setup, me, Out32<I>(metadata.local_to_global->get_data(), sz[1] + sz[5])));
             metadata.overlap_row = gko::Array<I>(
                 host, metadata.local_to_global->get_data() + sz[0],
                 metadata.local_to_global->get_data() + sz[1]);
             if (permute && metadata.global_size <= kMaterializeLimit) {
                 metadata.permutation = std::make_shared<gko::Array<I>>(host, metadata.global_size);
                 metadata.i_permutation = std::make_shared<gko::Array<I>>(host, metadata.global_size);
-                B200_CHECK(schwz_b200_setup_permutation(D.setup, metadata.permutation->get_data(),
-                                                        metadata.i_permutation->get_data()));
+                B200_CHECK(schwz_b200_setup_permutation(
+                    D.setup, Out32<I>(metadata.permutation->get_data(), metadata.global_size),
+                    Out32<I>(metadata.i_permutation->get_data(), metadata.global_size)));
             }
             local_matrix = gko::matrix::Csr<V, I>::create(host, gko::dim<2>(sz[1]), sz[3]);
             interface_matrix = gko::matrix::Csr<V, I>::create(
                 host, sz[4] > 0 ? gko::dim<2>(sz[1]) : gko::dim<2>(0), sz[4]);
             if ((gko::size_type)sz[1] <= kMaterializeLimit / 8 || settings.print_matrices) {
                 local_matrix->allocate();
-                B200_CHECK(schwz_b200_setup_local_matrix(D.setup, me, local_matrix->get_row_ptrs(),
-                                                         local_matrix->get_col_idxs(),
-                                                         local_matrix->get_values()));
+                B200_CHECK(schwz_b200_setup_local_matrix(
+                    D.setup, me, Out32<I>(local_matrix->get_row_ptrs(), sz[1] + 1),
+                    Out32<I>(local_matrix->get_col_idxs(), sz[3]), local_matrix->get_values()));
                 interface_matrix->allocate();
                 B200_CHECK(schwz_b200_setup_interface_matrix(
-                    D.setup, me, interface_matrix->get_row_ptrs(), interface_matrix->get_col_idxs(),
+                    D.setup, me,
+                    Out32<I>(interface_matrix->get_row_ptrs(), sz[4] > 0 ? sz[1] + 1 : 1),
+                    Out32<I>(interface_matrix->get_col_idxs(), sz[4]),
                     interface_matrix->get_values()));
             }
         }
@@ -851,8 +895,9 @@ void SolverRAS<V, I, M>::setup_comm_buffers()
             B200_CHECK(schwz_b200_setup_sizes(D.setup, me, sz));
             cs.num_neighbors_in = (int)sz[6];
             cs.num_neighbors_out = (int)sz[7];
-            B200_CHECK(schwz_b200_setup_neighbors(D.setup, me, cs.neighbors_in->get_data(),
-                                                  cs.neighbors_out->get_data()));
+            B200_CHECK(schwz_b200_setup_neighbors(
+                D.setup, me, Out32<I>(cs.neighbors_in->get_data(), std::max<int64_t>(sz[6], 1)),
+                Out32<I>(cs.neighbors_out->get_data(), std::max<int64_t>(sz[7], 1))));
             cs.recv.assign(P, 0);
             cs.send.assign(P, 0);
             for (int j = 0; j < cs.num_neighbors_in; ++j) {
@@ -861,7 +906,7 @@ void SolverRAS<V, I, M>::setup_comm_buffers()
                 cs.list_storage.emplace_back(cnt + 1);
                 auto &l = cs.list_storage.back();
                 l[0] = cnt;
-                B200_CHECK(schwz_b200_setup_get_list(D.setup, me, j, l.data() + 1));
+                B200_CHECK(schwz_b200_setup_get_list(D.setup, me, j, Out32<I>(l.data() + 1, cnt)));
                 cs.recv[cs.neighbors_in->get_data()[j]] = cnt;
             }
             for (int j = 0; j < cs.num_neighbors_out; ++j) {
@@ -870,7 +915,7 @@ void SolverRAS<V, I, M>::setup_comm_buffers()
                 cs.list_storage.emplace_back(cnt + 1);
                 auto &l = cs.list_storage.back();
                 l[0] = cnt;
-                B200_CHECK(schwz_b200_setup_put_list(D.setup, me, j, l.data() + 1));
+                B200_CHECK(schwz_b200_setup_put_list(D.setup, me, j, Out32<I>(l.data() + 1, cnt)));
                 cs.send[cs.neighbors_out->get_data()[j]] = cnt;
             }
             for (int j = 0; j < cs.num_neighbors_in; ++j)
@@ -879,8 +924,9 @@ void SolverRAS<V, I, M>::setup_comm_buffers()
                 cs.global_put->get_data()[j] = cs.local_put->get_data()[j] =
                     cs.list_storage[cs.num_neighbors_in + j].data();
             // A5 displacement tables (source/restricted_schwarz.cpp:624-658)
-            B200_CHECK(schwz_b200_setup_displacements(D.setup, me, cs.put_displacements->get_data(),
-                                                      cs.get_displacements->get_data()));
+            B200_CHECK(schwz_b200_setup_displacements(
+                D.setup, me, Out32<I>(cs.put_displacements->get_data(), P + 1),
+                Out32<I>(cs.get_displacements->get_data(), P + 1)));
             // the device object: local + interface matrices, vectors, mailbox
             schwz_ras_options o{};
             o.tolerance = metadata.tolerance;
@@ -997,5 +1043,16 @@ template class SchwarzBase<double, gko::int32, double>;
 template class SchwarzBase<double, gko::int32, float>;
 template class SolverRAS<double, gko::int32, double>;
 template class SolverRAS<double, gko::int32, float>;
+// IndexType = int64 (include/settings.hpp:533-537 of the reference instantiates it too): the
+// host-side index sets are handed out as int64, the device side stays int32 (N < 2^31)
+template class Initialize<double, gko::int64>;
+template class Communicate<double, gko::int64, double>;
+template class Communicate<double, gko::int64, float>;
+template class Solve<double, gko::int64, double>;
+template class Solve<double, gko::int64, float>;
+template class SchwarzBase<double, gko::int64, double>;
+template class SchwarzBase<double, gko::int64, float>;
+template class SolverRAS<double, gko::int64, double>;
+template class SolverRAS<double, gko::int64, float>;
 
 }  // namespace schwz

@@ -142,6 +142,22 @@ def test_local_precond_flag(tmp_path, orc, precond, banner):
     assert m and float(m.group(1)) < 5e-6
 
 
+def test_int64_index_type(tmp_path):
+    """SolverRAS<double, int64> (include/settings.hpp:533-537 instantiates it): same run, index sets
+    handed out as int64."""
+    args = ["--executor=cuda", "--explicit_laplacian", "--set_1d_laplacian_size=40",
+            "--partition=regular2d", "--enable_global_check", "--num_iters=400",
+            "--num_subdomains=4", "--write_comm_data"]
+    a = _run(args, tmp_path)
+    b = _run(args + ["--index_bits=64"], tmp_path)
+    pick = lambda out: sorted(l for l in out.splitlines()                       # noqa: E731
+                              if "converged in" in l or "local problem size" in l)
+    assert pick(a) == pick(b) and len(pick(a)) == 8
+    ra = re.search(r"relative residual norm of solution ([0-9.eE+-]+)", a).group(1)
+    rb = re.search(r"relative residual norm of solution ([0-9.eE+-]+)", b).group(1)
+    assert ra == rb
+
+
 def test_error_convention(tmp_path):
     p = subprocess.run([BIN, "--executor=omp", "--explicit_laplacian", "--num_subdomains=1"],
                        cwd=tmp_path, capture_output=True, text=True, timeout=60)
