@@ -722,8 +722,48 @@ void Setup::build_index_sets()
             R.get_disp[q] = out_pref[q][me];
         }
     }
+    std::vector<int32_t>().swap(g2l_);   // the dense scratch (4 N bytes) is not needed any more
     have_index_ = true;
 }
+
+// global id -> 1 + local slot of one subdomain (0 = absent) without the shared dense scratch of
+// the index-set pass: the own block is a contiguous id range, the few thousand overlap / halo ids
+// sit in a small open-addressing table.  Makes build_matrices / compact_interface re-entrant,
+// so the ranks of one process can build their local matrices side by side.
+namespace {
+struct LocalIndex {
+    int32_t first = 0, own = 0;
+    uint32_t mask = 0;
+    std::vector<int32_t> key, val;
+    LocalIndex(int32_t first_, int32_t own_, size_t n_ext) : first(first_), own(own_)
+    {
+        size_t cap = 16;
+        while (cap < 2 * n_ext + 1) cap <<= 1;
+        mask = (uint32_t)cap - 1;
+        key.assign(cap, -1);
+        val.assign(cap, 0);
+    }
+    static uint32_t hash(int32_t g) { return (uint32_t)g * 2654435761u; }
+    void put(int32_t g, int32_t v)
+    {
+        uint32_t h = hash(g) & mask;
+        while (key[h] != -1) h = (h + 1) & mask;
+        key[h] = g;
+        val[h] = v;
+    }
+    int32_t operator()(int32_t g) const
+    {
+        const uint32_t d = (uint32_t)(g - first);
+        if (d < (uint32_t)own) return 1 + (int32_t)d;
+        uint32_t h = hash(g) & mask;
+        while (key[h] != -1) {
+            if (key[h] == g) return val[h];
+            h = (h + 1) & mask;
+        }
+        return 0;
+    }
+};
+}  // namespace
 
 // Local and interface matrices of one subdomain.
 void Setup::build_matrices(int32_t me)
@@ -735,7 +775,8 @@ void Setup::build_matrices(int32_t me)
     std::vector<int32_t> c(g.max_row), lc(g.max_row), ic(g.max_row);
     std::vector<double> v(g.max_row), lv(g.max_row), iv(g.max_row);
     // g2l as it is when the reference builds the matrices: own + overlap only
-    for (int32_t k = 0; k < R.local_size_x; ++k) g2l_[R.l2g[k]] = 1 + k;
+    LocalIndex g2l(first_row_[me], R.local_size, (size_t)R.overlap_size);
+    for (int32_t k = R.local_size; k < R.local_size_x; ++k) g2l.put(R.l2g[k], 1 + k);
     HostCsr &Lm = R.local;
     HostCsr &Im = R.iface;
     Lm = HostCsr();
@@ -749,7 +790,7 @@ void Setup::build_matrices(int32_t me)
         const int len = g.row(R.l2g[k], c.data(), v.data());
         int nl = 0, ni = 0;
         for (int j = 0; j < len; ++j) {
-            const int32_t loc = g2l_[c[j]];
+            const int32_t loc = g2l(c[j]);
             if (loc != 0) {
                 lc[nl] = loc - 1;
                 lv[nl++] = v[j];
@@ -774,7 +815,6 @@ void Setup::build_matrices(int32_t me)
         Im.nrows = Im.ncols = 0;                // empty 0x0 matrix (:231)
         Im.rp.assign(1, 0);
     }
-    for (int32_t k = 0; k < R.local_size_x; ++k) g2l_[R.l2g[k]] = 0;
     R.have_matrix = true;
 }
 
@@ -789,25 +829,24 @@ void Setup::release(int32_t r)
 void Setup::compact_interface(int32_t me, HostCsr &out) const
 {
     const RankLayout &R = ranks_[me];
-    auto &g2l = const_cast<std::vector<int32_t> &>(g2l_);
     out = HostCsr();
     out.nrows = R.overlap_size;
     out.ncols = R.local_size_x + R.n_halo;
     out.rp.assign((size_t)R.overlap_size + 1, 0);
     if (R.iface.nrows == 0) return;
-    for (int32_t k = R.local_size_x; k < R.local_size_x + R.n_halo; ++k) g2l[R.l2g[k]] = 1 + k;
+    LocalIndex g2l(0, 0, (size_t)R.n_halo);   // interface columns are halo ids only
+    for (int32_t k = R.local_size_x; k < R.local_size_x + R.n_halo; ++k) g2l.put(R.l2g[k], 1 + k);
     out.ci.reserve(R.iface.ci.size());
     out.v = R.iface.v;
     for (int32_t k = 0; k < R.overlap_size; ++k) {
         const int32_t row = R.local_size + k;
         for (int32_t q = R.iface.rp[row]; q < R.iface.rp[row + 1]; ++q) {
-            const int32_t loc = g2l[R.iface.ci[q]];
+            const int32_t loc = g2l(R.iface.ci[q]);
             if (loc == 0) throw std::runtime_error("interface column outside the halo layer");
             out.ci.push_back(loc - 1);
         }
         out.rp[k + 1] = (int32_t)out.ci.size();
     }
-    for (int32_t k = R.local_size_x; k < R.local_size_x + R.n_halo; ++k) g2l[R.l2g[k]] = 0;
 }
 
 }  // namespace schwz_b200

@@ -8,6 +8,7 @@
 #include <condition_variable>
 #include <functional>
 #include <mutex>
+#include <stdexcept>
 #include <thread>
 #include <vector>
 
@@ -67,7 +68,10 @@ public:
     std::vector<void *> &slots(int which)
     {
         std::lock_guard<std::mutex> lk(m_);
-        if ((int)tables_.size() <= which) tables_.resize(which + 1);
+        // sized once for every slot kind: a later resize would move the tables other ranks
+        // hold references to
+        if (tables_.empty()) tables_.resize(16);
+        if ((int)tables_.size() <= which) throw std::runtime_error("slot table index out of range");
         if ((int)tables_[which].size() < size_) tables_[which].resize(size_, nullptr);
         return tables_[which];
     }

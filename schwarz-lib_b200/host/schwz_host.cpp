@@ -831,10 +831,11 @@ void SolverRAS<V, I, M>::setup_local_matrices(
     }
     G.barrier();
     D.setup = (schwz_setup *)G.slots(kSlotSetup)[0];
-    // the index-set object is not re-entrant: ranks read their part in turn
+    // the index sets were built once by rank 0; reading them and building the local matrices is
+    // re-entrant, so the ranks work side by side
     auto host = settings.executor->get_master();
-    for (int turn = 0; turn < P; ++turn) {
-        if (turn == me) {
+    for (int turn = me; turn == me; ++turn) {
+        {
             B200_CHECK(schwz_b200_setup_first_row(D.setup,
                                                   Out32<I>(metadata.first_row->get_data(), P + 1)));
             int64_t sz[8];
@@ -872,8 +873,8 @@ void SolverRAS<V, I, M>::setup_local_matrices(
                     interface_matrix->get_values()));
             }
         }
-        G.barrier();
     }
+    G.barrier();
 }
 
 template <typename V, typename I, typename M>
@@ -889,8 +890,8 @@ void SolverRAS<V, I, M>::setup_comm_buffers()
     auto &cs = this->comm_struct;
     const int me = metadata.my_rank;
     const int P = (int)metadata.num_subdomains;
-    for (int turn = 0; turn < P; ++turn) {
-        if (turn == me) {
+    for (int turn = me; turn == me; ++turn) {   // every rank at once (the setup object is re-entrant)
+        {
             int64_t sz[8];
             B200_CHECK(schwz_b200_setup_sizes(D.setup, me, sz));
             cs.num_neighbors_in = (int)sz[6];
@@ -963,8 +964,8 @@ void SolverRAS<V, I, M>::setup_comm_buffers()
             G.slots(kSlotRas)[me] = D.ras;
             G.slots(kSlotCtx)[me] = D.ctx;
         }
-        G.barrier();
     }
+    G.barrier();
 }
 
 template <typename V, typename I, typename M>
