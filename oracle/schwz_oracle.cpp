@@ -6,15 +6,20 @@
 // __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
 // may load it.  The product (schwarz-lib_b200/) never links or calls it.
 //
-// PARITY STATUS: "parity unpinned" for the floating-point part.  The reference
-// ships no tests, golden vectors or fixtures (TESTING.md:1-2) and cannot be
-// built here (needs MPI + Ginkgo branch expt-develop + gflags),
-// so this restatement is pinned only by (i) hand-derivable integer known
-// answers for the index sets, (ii) scipy cross-checks of
-// the local solves, (iii) the mathematical fixed point of the iteration.
-// The integer part (A1-A6) follows in-tree reference code literally and is
-// deterministic; the floating part follows Ginkgo semantics restated from the
-// reference's call sites (Ginkgo itself is not under /root/reference).
+// PARITY STATUS: pinned.  oracle/_ref is the reference's own source/*.cpp compiled unmodified
+// (oracle/Makefile) against stand-ins for MPI, Ginkgo and the generated config header
+// (oracle/ref_shim/); tests/test_ref_pinning.py, test_ref_pinning_random.py and
+// test_precond_pinning.py require this restatement to reproduce that reference run bit for
+// bit: partition, permutation, permuted matrix, overlap / halo numbering, local and interface
+// matrices, halo lists, displacement tables, the iterate after every exchange, the residual
+// histories and the stopping iteration - on the Laplacian configs, ani4_crop with the
+// reference's own METIS call, seeded random matrices, and with the local preconditioners.
+// What stays unpinned, by construction: the bit patterns of upstream Ginkgo's own kernels
+// (Ginkgo is not under /root/reference; its arithmetic is restated from the call sites and from
+// the upstream reference-executor kernels), and CHOLMOD / UMFPACK (absent:
+// the factorised variants are pinned mathematically, L L^T = P A P^T and P A Q = L U).
+// Earlier anchors stay: SURVEY.md Appendix E known answers, scipy cross-checks of the local
+// solves, the fixed point of the iteration.
 //
 // Every function cites the reference file:line it follows (paths relative to
 // /root/reference).
