@@ -167,9 +167,11 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------
-# CPU arm: the oracle port (oracle/schwz_oracle.cpp) on the host cores.  The
-# reference binary cannot be built here (MPI + Ginkgo expt-develop + gflags),
-# see DESIGN.md, so kind = "port".
+# CPU arm: the oracle port (oracle/schwz_oracle.cpp, pinned bit for bit to oracle/_ref = the
+# reference's own sources on stand-ins for MPI / Ginkgo) on the host cores, kind = "port".
+# oracle/_ref itself has no bounded sample of cfg2 (it replicates the 4.3 GB global matrix on
+# every rank and sets up through std::map walks); where both run - 1024^2, 8 strips - the port
+# and the reference's own loop take the same time per outer iteration.
 # ----------------------------------------------------------------------------
 _CPU_CACHE = {}
 

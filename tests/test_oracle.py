@@ -1,8 +1,8 @@
-"""Pins the CPU oracle: (i) SURVEY Appendix E known answers (tests/golden/
+"""Independent anchors of the CPU oracle: (i) SURVEY Appendix E known answers (tests/golden/
 appendix_e.json), (ii) scipy cross-checks of its local solves, (iii) the fixed
 point of the iteration.  The reference itself ships no tests or golden vectors
-(TESTING.md:1-2), so these are the strongest pins available ("parity unpinned"
-for the floating-point part)."""
+(TESTING.md:1-2); the pin against the reference's own code is tests/test_ref_pinning*.py and
+tests/test_precond_pinning.py (oracle/_ref), these tests are the cross-checks beside it."""
 import json
 import os
 
