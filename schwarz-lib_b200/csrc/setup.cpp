@@ -599,8 +599,62 @@ Setup::Setup(std::unique_ptr<RowSource> base, int32_t P, int32_t partition_kind,
     for (int32_t p = 0; p < P; ++p) ranks_[p].local_size = local_p_size_[p];
 }
 
-// Index set of one subdomain.  g2l_ is the
-// shared dense scratch; it is restored to all-zero before returning.
+// global id -> 1 + local slot of one subdomain (0 = absent) without the shared dense scratch of
+// the index-set pass: the own block is a contiguous id range, the few thousand overlap / halo ids
+// sit in a small open-addressing table.  Makes index_set / build_matrices / compact_interface
+// re-entrant, so the subdomains of one process are set up side by side.
+namespace {
+struct LocalIndex {
+    int32_t first = 0, own = 0;
+    uint32_t mask = 0;
+    std::vector<int32_t> key, val;
+    size_t used = 0;
+    LocalIndex(int32_t first_, int32_t own_, size_t n_ext) : first(first_), own(own_)
+    {
+        size_t cap = 16;
+        while (cap < 2 * n_ext + 1) cap <<= 1;
+        mask = (uint32_t)cap - 1;
+        key.assign(cap, -1);
+        val.assign(cap, 0);
+    }
+    static uint32_t hash(int32_t g) { return (uint32_t)g * 2654435761u; }
+    void grow()
+    {
+        std::vector<int32_t> k2, v2;
+        k2.swap(key);
+        v2.swap(val);
+        const size_t cap = 2 * k2.size();
+        mask = (uint32_t)cap - 1;
+        key.assign(cap, -1);
+        val.assign(cap, 0);
+        used = 0;
+        for (size_t i = 0; i < k2.size(); ++i)
+            if (k2[i] != -1) put(k2[i], v2[i]);
+    }
+    void put(int32_t g, int32_t v)
+    {
+        if (2 * (used + 1) > key.size()) grow();
+        uint32_t h = hash(g) & mask;
+        while (key[h] != -1) h = (h + 1) & mask;
+        key[h] = g;
+        val[h] = v;
+        ++used;
+    }
+    int32_t operator()(int32_t g) const
+    {
+        const uint32_t d = (uint32_t)(g - first);
+        if (d < (uint32_t)own) return 1 + (int32_t)d;
+        uint32_t h = hash(g) & mask;
+        while (key[h] != -1) {
+            if (key[h] == g) return val[h];
+            h = (h + 1) & mask;
+        }
+        return 0;
+    }
+};
+}  // namespace
+
+// Index set of one subdomain.
 void Setup::index_set(int32_t me)
 {
     RankLayout &R = ranks_[me];
@@ -612,19 +666,19 @@ void Setup::index_set(int32_t me)
     l2g.reserve((size_t)R.local_size + 1024);
     int32_t num = 0;
     for (int32_t i = first_row_[me]; i < first_row_[me + 1]; ++i) {
-        g2l_[i] = 1 + num;
         l2g.push_back(i);
         ++num;
     }
+    LocalIndex g2l(first_row_[me], R.local_size, 1024);
     int32_t old = 0;
     for (int k = 1; k < overlap_; ++k) {
         const int32_t now = num;
         for (int32_t i = old; i < now; ++i) {
             const int len = g.row(l2g[i], c.data(), v.data());
             for (int j = 0; j < len; ++j)
-                if (g2l_[c[j]] == 0) {
+                if (g2l(c[j]) == 0) {
                     l2g.push_back(c[j]);
-                    g2l_[c[j]] = 1 + num;
+                    g2l.put(c[j], 1 + num);
                     ++num;
                 }
         }
@@ -638,7 +692,7 @@ void Setup::index_set(int32_t me)
     for (int32_t k = R.local_size; k < R.local_size_x && !have_iface; ++k) {
         const int len = g.row(l2g[k], c.data(), v.data());
         for (int j = 0; j < len; ++j)
-            if (g2l_[c[j]] == 0) {
+            if (g2l(c[j]) == 0) {
                 have_iface = true;
                 break;
             }
@@ -648,9 +702,9 @@ void Setup::index_set(int32_t me)
         for (int32_t i = old; i < now; ++i) {
             const int len = g.row(l2g[i], c.data(), v.data());
             for (int j = 0; j < len; ++j)
-                if (g2l_[c[j]] == 0) {
+                if (g2l(c[j]) == 0) {
                     l2g.push_back(c[j]);
-                    g2l_[c[j]] = 1 + num;
+                    g2l.put(c[j], 1 + num);
                     ++num;
                 }
         }
@@ -673,14 +727,14 @@ void Setup::index_set(int32_t me)
         }
         pos = end;
     }
-    for (int32_t id : l2g) g2l_[id] = 0;
     R.have_index = true;
 }
 
 void Setup::build_index_sets()
 {
     if (have_index_) return;
-    g2l_.assign((size_t)N_, 0);
+    // every subdomain on its own (no shared scratch): side by side on the host cores
+#pragma omp parallel for schedule(dynamic, 1)
     for (int32_t p = 0; p < P_; ++p) index_set(p);
     // owner side of the handshake (:400-472): put-list p -> q is q's get-list
     // from p; neighbours_out ascending
@@ -722,48 +776,8 @@ void Setup::build_index_sets()
             R.get_disp[q] = out_pref[q][me];
         }
     }
-    std::vector<int32_t>().swap(g2l_);   // the dense scratch (4 N bytes) is not needed any more
     have_index_ = true;
 }
-
-// global id -> 1 + local slot of one subdomain (0 = absent) without the shared dense scratch of
-// the index-set pass: the own block is a contiguous id range, the few thousand overlap / halo ids
-// sit in a small open-addressing table.  Makes build_matrices / compact_interface re-entrant,
-// so the ranks of one process can build their local matrices side by side.
-namespace {
-struct LocalIndex {
-    int32_t first = 0, own = 0;
-    uint32_t mask = 0;
-    std::vector<int32_t> key, val;
-    LocalIndex(int32_t first_, int32_t own_, size_t n_ext) : first(first_), own(own_)
-    {
-        size_t cap = 16;
-        while (cap < 2 * n_ext + 1) cap <<= 1;
-        mask = (uint32_t)cap - 1;
-        key.assign(cap, -1);
-        val.assign(cap, 0);
-    }
-    static uint32_t hash(int32_t g) { return (uint32_t)g * 2654435761u; }
-    void put(int32_t g, int32_t v)
-    {
-        uint32_t h = hash(g) & mask;
-        while (key[h] != -1) h = (h + 1) & mask;
-        key[h] = g;
-        val[h] = v;
-    }
-    int32_t operator()(int32_t g) const
-    {
-        const uint32_t d = (uint32_t)(g - first);
-        if (d < (uint32_t)own) return 1 + (int32_t)d;
-        uint32_t h = hash(g) & mask;
-        while (key[h] != -1) {
-            if (key[h] == g) return val[h];
-            h = (h + 1) & mask;
-        }
-        return 0;
-    }
-};
-}  // namespace
 
 // Local and interface matrices of one subdomain.
 void Setup::build_matrices(int32_t me)

@@ -5,8 +5,8 @@
 // setup_comm_buffers / setup_windows (source/restricted_schwarz.cpp:56-711)
 // without replicating the global matrix per subdomain: rows come from a
 // RowSource (generated stencil, stored CSR, or either one seen through the
-// partition permutation), and one dense global->local scratch array is shared
-// by all subdomains of the process.
+// partition permutation); global->local lookups go through a small per-call index (own range +
+// hash of the overlap / halo ids), so the subdomains of a process share no scratch.
 #pragma once
 #include <cstdint>
 #include <memory>
@@ -97,7 +97,6 @@ private:
     bool permuted_ = false;
     std::vector<int32_t> first_row_, perm_, iperm_, local_p_size_;
     std::vector<RankLayout> ranks_;
-    std::vector<int32_t> g2l_;   // shared scratch, all zero between uses
     bool have_index_ = false;
 };
 
