@@ -4,7 +4,11 @@
 // SolverRAS::initialize() / run(); main() starts one host thread per subdomain
 // where the reference is started as `mpirun -n P`.
 #include <cmath>
+#include <functional>
+#include <initializer_list>
 #include <iostream>
+#include <string>
+#include <utility>
 
 #include "bench_base.hpp"
 
@@ -17,94 +21,113 @@ private:
     void solve(MPI_Comm mpi_communicator);
 };
 
+namespace {
+
+// A string-valued flag selects one entry of a small table; an unknown value leaves the settings
+// at their defaults, which is what the if / else-if chains of the reference amount to
+// (benchmarking/bench_ras.cpp:72-149).
+template <typename Action>
+void select(const std::string &value, std::initializer_list<std::pair<const char *, Action>> table)
+{
+    for (const auto &entry : table)
+        if (value == entry.first) {
+            entry.second();
+            return;
+        }
+}
+using Apply = std::function<void()>;
+
+void wire_communication(schwz::Settings &st)
+{
+    auto &c = st.comm_settings;
+    c.enable_onesided = FLAGS_enable_onesided;
+    c.enable_one_by_one = FLAGS_enable_one_by_one;
+    c.enable_overlap = FLAGS_enable_comm_overlap;
+    select<Apply>(FLAGS_remote_comm_type, {{"put", [&] { c.enable_put = true, c.enable_get = false; }},
+                                          {"get", [&] { c.enable_put = false, c.enable_get = true; }}});
+    select<Apply>(FLAGS_flush_type,
+                  {{"flush-all", [&] { c.enable_flush_all = true; }},
+                   {"flush-local", [&] { c.enable_flush_all = false, c.enable_flush_local = true; }}});
+    select<Apply>(FLAGS_lock_type,
+                  {{"lock-all", [&] { c.enable_lock_all = true; }},
+                   {"lock-local", [&] { c.enable_lock_all = false, c.enable_lock_local = true; }}});
+}
+
+void wire_convergence(schwz::Settings &st)
+{
+    auto &c = st.convergence_settings;
+    c.enable_global_check = FLAGS_enable_global_check;
+    c.enable_global_check_iter_offset = FLAGS_enable_global_check_iter_offset;
+    c.put_all_local_residual_norms = FLAGS_enable_put_all_local_residual_norms;
+    select<Apply>(FLAGS_global_convergence_type,
+                  {{"centralized-tree", [&] { c.enable_global_simple_tree = true; }},
+                   {"decentralized", [&] {
+                        c.enable_decentralized_leader_election = true;
+                        c.enable_accumulate = FLAGS_enable_decentralized_accumulate;
+                    }}});
+}
+
+void wire_problem_and_local_solver(schwz::Settings &st)
+{
+    using S = schwz::Settings;
+    st.matrix_filename = FLAGS_matrix_filename;
+    st.explicit_laplacian = FLAGS_explicit_laplacian;
+    st.enable_random_rhs = FLAGS_enable_random_rhs;
+    st.overlap = FLAGS_overlap;
+    st.non_symmetric_matrix = FLAGS_non_symmetric_matrix;
+    st.restart_iter = FLAGS_restart_iter;
+    st.naturally_ordered_factor = FLAGS_factor_ordering_natural;
+    st.reorder = FLAGS_local_reordering;
+    st.factorization = FLAGS_local_factorization;
+    select<Apply>(FLAGS_partition,
+                  {{"regular", [&] { st.partition = S::partition_settings::partition_regular; }},
+                   {"regular2d", [&] { st.partition = S::partition_settings::partition_regular2d; }},
+                   {"metis", [&] {
+                        st.partition = S::partition_settings::partition_metis;
+                        st.metis_objtype = FLAGS_metis_objtype;
+                    }}});
+    using L = S::local_solver_settings;
+    select<Apply>(FLAGS_local_solver,
+                  {{"iterative-ginkgo", [&] { st.local_solver = L::iterative_solver_ginkgo; }},
+                   {"direct-ginkgo", [&] { st.local_solver = L::direct_solver_ginkgo; }},
+                   {"direct-cholmod", [&] { st.local_solver = L::direct_solver_cholmod; }},
+                   {"direct-umfpack", [&] { st.local_solver = L::direct_solver_umfpack; }}});
+    // output switches
+    st.write_debug_out = FLAGS_enable_debug_write;
+    st.write_perm_data = FLAGS_write_perm_data;
+    st.write_iters_and_residuals = FLAGS_write_iters_and_residuals;
+    st.print_matrices = FLAGS_print_matrices;
+    st.shifted_iter = FLAGS_shifted_iter;
+    st.debug_print = FLAGS_debug;
+    // launcher additions (not in the reference)
+    st.num_devices = FLAGS_num_devices;
+    st.laplacian_dim = FLAGS_laplacian_dim;
+}
+
+}  // namespace
+
 template <typename ValueType, typename IndexType>
 void BenchRas<ValueType, IndexType>::solve(MPI_Comm mpi_communicator)
 {
-    schwz::Metadata<ValueType, IndexType> metadata;
+    // flags -> Settings / Metadata, field for field what benchmarking/bench_ras.cpp:47-150 sets
     schwz::Settings settings(FLAGS_executor);
+    wire_communication(settings);
+    wire_convergence(settings);
+    wire_problem_and_local_solver(settings);
 
+    schwz::Metadata<ValueType, IndexType> metadata;
     metadata.mpi_communicator = mpi_communicator;
-    MPI_Comm_rank(metadata.mpi_communicator, &metadata.my_rank);
-    MPI_Comm_size(metadata.mpi_communicator, &metadata.comm_size);
-    metadata.tolerance = FLAGS_set_tol;
-    metadata.max_iters = FLAGS_num_iters;
+    MPI_Comm_rank(mpi_communicator, &metadata.my_rank);
+    MPI_Comm_size(mpi_communicator, &metadata.comm_size);
     metadata.num_subdomains = metadata.comm_size;
     metadata.num_threads = FLAGS_num_threads;
     metadata.oned_laplacian_size = FLAGS_set_1d_laplacian_size;
-
-    settings.write_debug_out = FLAGS_enable_debug_write;
-    settings.write_perm_data = FLAGS_write_perm_data;
-    settings.write_iters_and_residuals = FLAGS_write_iters_and_residuals;
-    settings.print_matrices = FLAGS_print_matrices;
-    settings.shifted_iter = FLAGS_shifted_iter;
-
-    settings.comm_settings.enable_onesided = FLAGS_enable_onesided;
-    if (FLAGS_remote_comm_type == "put") {
-        settings.comm_settings.enable_put = true;
-        settings.comm_settings.enable_get = false;
-    } else if (FLAGS_remote_comm_type == "get") {
-        settings.comm_settings.enable_put = false;
-        settings.comm_settings.enable_get = true;
-    }
-    settings.comm_settings.enable_one_by_one = FLAGS_enable_one_by_one;
-    settings.comm_settings.enable_overlap = FLAGS_enable_comm_overlap;
-    if (FLAGS_flush_type == "flush-all") {
-        settings.comm_settings.enable_flush_all = true;
-    } else if (FLAGS_flush_type == "flush-local") {
-        settings.comm_settings.enable_flush_all = false;
-        settings.comm_settings.enable_flush_local = true;
-    }
-    if (FLAGS_lock_type == "lock-all") {
-        settings.comm_settings.enable_lock_all = true;
-    } else if (FLAGS_lock_type == "lock-local") {
-        settings.comm_settings.enable_lock_all = false;
-        settings.comm_settings.enable_lock_local = true;
-    }
-
-    settings.convergence_settings.put_all_local_residual_norms = FLAGS_enable_put_all_local_residual_norms;
-    settings.convergence_settings.enable_global_check_iter_offset = FLAGS_enable_global_check_iter_offset;
-    settings.convergence_settings.enable_global_check = FLAGS_enable_global_check;
-    if (FLAGS_global_convergence_type == "centralized-tree") {
-        settings.convergence_settings.enable_global_simple_tree = true;
-    } else if (FLAGS_global_convergence_type == "decentralized") {
-        settings.convergence_settings.enable_decentralized_leader_election = true;
-        settings.convergence_settings.enable_accumulate = FLAGS_enable_decentralized_accumulate;
-    }
-
+    metadata.tolerance = FLAGS_set_tol;
+    metadata.max_iters = FLAGS_num_iters;
     metadata.local_solver_tolerance = FLAGS_local_tol;
-    metadata.local_precond = FLAGS_local_precond;
     metadata.local_max_iters = FLAGS_local_max_iters;
-    settings.non_symmetric_matrix = FLAGS_non_symmetric_matrix;
-    settings.restart_iter = FLAGS_restart_iter;
+    metadata.local_precond = FLAGS_local_precond;
     metadata.precond_max_block_size = FLAGS_precond_max_block_size;
-    settings.matrix_filename = FLAGS_matrix_filename;
-    settings.explicit_laplacian = FLAGS_explicit_laplacian;
-    settings.enable_random_rhs = FLAGS_enable_random_rhs;
-    settings.overlap = FLAGS_overlap;
-    settings.naturally_ordered_factor = FLAGS_factor_ordering_natural;
-    settings.reorder = FLAGS_local_reordering;
-    settings.factorization = FLAGS_local_factorization;
-    if (FLAGS_partition == "metis") {
-        settings.partition = schwz::Settings::partition_settings::partition_metis;
-        settings.metis_objtype = FLAGS_metis_objtype;
-    } else if (FLAGS_partition == "regular") {
-        settings.partition = schwz::Settings::partition_settings::partition_regular;
-    } else if (FLAGS_partition == "regular2d") {
-        settings.partition = schwz::Settings::partition_settings::partition_regular2d;
-    }
-    if (FLAGS_local_solver == "iterative-ginkgo") {
-        settings.local_solver = schwz::Settings::local_solver_settings::iterative_solver_ginkgo;
-    } else if (FLAGS_local_solver == "direct-cholmod") {
-        settings.local_solver = schwz::Settings::local_solver_settings::direct_solver_cholmod;
-    } else if (FLAGS_local_solver == "direct-umfpack") {
-        settings.local_solver = schwz::Settings::local_solver_settings::direct_solver_umfpack;
-    } else if (FLAGS_local_solver == "direct-ginkgo") {
-        settings.local_solver = schwz::Settings::local_solver_settings::direct_solver_ginkgo;
-    }
-    settings.debug_print = FLAGS_debug;
-    // launcher additions
-    settings.num_devices = FLAGS_num_devices;
-    settings.laplacian_dim = FLAGS_laplacian_dim;
 
     std::shared_ptr<gko::matrix::Dense<ValueType>> explicit_laplacian_solution;
 
