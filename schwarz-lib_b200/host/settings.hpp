@@ -23,75 +23,47 @@ struct Settings {
     std::shared_ptr<gko::Executor> executor = gko::ReferenceExecutor::create();
     std::shared_ptr<void> cuda_device_guard;           // RAII device guard in the reference
 
-    // -- partitioning / problem ------------------------------------------------
-    enum partition_settings {
-        partition_regular = 0x0,
-        partition_regular2d = 0x4,
-        partition_metis = 0x1,
-        partition_zoltan = 0x2,
-        partition_custom = 0x3
-    };
-    partition_settings partition = partition_settings::partition_regular;
+    // -- problem and partitioning (values of the enumerators as in the reference) ----
+    enum partition_settings { partition_regular = 0, partition_metis = 1, partition_zoltan = 2,
+                              partition_custom = 3, partition_regular2d = 4 };
+    partition_settings partition = partition_regular;
+    std::string matrix_filename = "null", metis_objtype;
     gko::int32 overlap = MINIMAL_OVERLAP;
-    std::string matrix_filename = "null";
-    bool explicit_laplacian = true;
-    bool use_mixed_precision = false;
-    bool enable_random_rhs = false;
-    bool print_matrices = false;
-    bool debug_print = false;
+    bool explicit_laplacian = true, enable_random_rhs = false, use_mixed_precision = false;
 
     // -- local solver ----------------------------------------------------------
-    enum local_solver_settings {
-        direct_solver_cholmod = 0x0,
-        direct_solver_umfpack = 0x5,
-        direct_solver_ginkgo = 0x1,
-        iterative_solver_ginkgo = 0x2,
-        iterative_solver_dealii = 0x3,
-        solver_custom = 0x4
-    };
-    local_solver_settings local_solver = local_solver_settings::iterative_solver_ginkgo;
-    bool non_symmetric_matrix = false;
+    enum local_solver_settings { direct_solver_cholmod = 0, direct_solver_ginkgo = 1,
+                                 iterative_solver_ginkgo = 2, iterative_solver_dealii = 3,
+                                 solver_custom = 4, direct_solver_umfpack = 5 };
+    local_solver_settings local_solver = iterative_solver_ginkgo;
+    std::string factorization = "cholmod", reorder;    // "cholmod" | "umfpack"; reorder is unused
+    bool non_symmetric_matrix = false, naturally_ordered_factor = false, use_precond = false;
     unsigned int restart_iter = 1u;
-    int reset_local_crit_iter = -1;
-    bool naturally_ordered_factor = false;
-    std::string metis_objtype;
-    bool use_precond = false;
+    int reset_local_crit_iter = -1;   // past this outer iteration: metadata.updated_max_iters
 
     // -- output ----------------------------------------------------------------
-    bool write_debug_out = false;
-    bool write_iters_and_residuals = false;
-    bool enable_logging = false;
-    bool write_perm_data = false;
+    bool print_matrices = false, debug_print = false, write_debug_out = false,
+         write_iters_and_residuals = false, write_perm_data = false, enable_logging = false;
     int shifted_iter = 1;
 
+    // halo exchange (all defaults as upstream: one-sided off, Get, flush-all, lock-all)
     struct comm_settings {
-        bool enable_onesided = false;
-        bool enable_overlap = false;
-        bool enable_put = false;
-        bool enable_get = true;
-        bool stage_through_host = false;
-        bool enable_one_by_one = false;
-        bool enable_flush_local = false;
-        bool enable_flush_all = true;
-        bool enable_lock_local = false;
-        bool enable_lock_all = true;
+        bool enable_onesided = false, enable_overlap = false, stage_through_host = false;
+        bool enable_put = false, enable_get = true, enable_one_by_one = false;
+        bool enable_flush_all = true, enable_flush_local = false;
+        bool enable_lock_all = true, enable_lock_local = false;
     };
     comm_settings comm_settings;
 
     struct convergence_settings {
+        bool enable_global_check = true, enable_global_check_iter_offset = false;
+        bool enable_global_simple_tree = false, enable_decentralized_leader_election = false,
+             enable_accumulate = false;
         bool put_all_local_residual_norms = true;
-        bool enable_global_simple_tree = false;
-        bool enable_decentralized_leader_election = false;
-        bool enable_global_check = true;
-        bool enable_accumulate = false;
-        bool enable_global_check_iter_offset = false;
-        enum local_convergence_crit { residual_based = 0x0, solution_based = 0x1 };
-        local_convergence_crit convergence_crit = local_convergence_crit::solution_based;
+        enum local_convergence_crit { residual_based = 0, solution_based = 1 };
+        local_convergence_crit convergence_crit = solution_based;
     };
     convergence_settings convergence_settings;
-
-    std::string factorization = "cholmod";
-    std::string reorder;
 
     // -- additions of this implementation (not in the reference) ---------------
     int num_devices = 0;       // 0 = all visible GPUs; subdomain s runs on GPU s % num_devices
@@ -103,55 +75,42 @@ struct Settings {
 template <typename ValueType, typename IndexType>
 struct Metadata {
     MPI_Comm mpi_communicator = MPI_COMM_WORLD;
+    int my_rank = 0, my_local_rank = 0, local_num_procs = 1, comm_size = 1, num_threads = 1;
 
-    gko::size_type global_size = 0;
-    gko::size_type oned_laplacian_size = 0;
-    gko::size_type local_size = 0;
-    gko::size_type local_size_x = 0;
-    gko::size_type local_size_o = 0;
-    gko::size_type overlap_size = 0;
-    gko::size_type num_subdomains = 1;
+    // sizes: global problem, generated-Laplacian edge, and this subdomain's own / own+overlap /
+    // "locally global" / overlap counts
+    gko::size_type global_size = 0, oned_laplacian_size = 0, num_subdomains = 1;
+    gko::size_type local_size = 0, local_size_x = 0, local_size_o = 0, overlap_size = 0;
 
-    int my_rank = 0;
-    int my_local_rank = 0;
-    int local_num_procs = 1;
-    int comm_size = 1;
-    int num_threads = 1;
-
-    IndexType iter_count = 0;
-    ValueType tolerance = 1e-6;
+    // outer iteration
+    IndexType iter_count = 0, max_iters = 100;
+    ValueType tolerance = 1e-6, current_residual_norm = -1.0, min_residual_norm = -1.0;
+    // local solve
     ValueType local_solver_tolerance = 1e-12;
-    IndexType max_iters = 100;
-    IndexType local_max_iters = -1;
-    IndexType updated_max_iters = -1;
+    IndexType local_max_iters = -1, updated_max_iters = -1;
     std::string local_precond = "null";
     unsigned int precond_max_block_size = 16;
-    ValueType current_residual_norm = -1.0;
-    ValueType min_residual_norm = -1.0;
 
     // (id, rank, last iteration, name, samples) per timed stage
     std::vector<std::tuple<int, int, int, std::string, std::vector<ValueType>>> time_struct;
     // (subdomain, [(from, count)], [(to, count)], #in, #out)
-    std::vector<std::tuple<int, std::vector<std::tuple<int, int>>, std::vector<std::tuple<int, int>>,
-                           int, int>>
-        comm_data_struct;
+    using neighbour_counts = std::vector<std::tuple<int, int>>;
+    std::vector<std::tuple<int, neighbour_counts, neighbour_counts, int, int>> comm_data_struct;
 
     struct post_process_data {
         std::vector<std::vector<ValueType>> global_residual_vector_out;
-        std::vector<ValueType> local_residual_vector_out;
-        std::vector<ValueType> local_converged_iter_count;
-        std::vector<ValueType> local_converged_resnorm;
-        std::vector<ValueType> local_timestamp;
+        std::vector<ValueType> local_residual_vector_out, local_converged_iter_count,
+            local_converged_resnorm, local_timestamp;
     };
     post_process_data post_process_data;
     double init_mpi_wtime = 0.0;
 
-    std::shared_ptr<gko::Array<IndexType>> global_to_local;
-    std::shared_ptr<gko::Array<IndexType>> local_to_global;
-    gko::Array<IndexType> overlap_row;
-    std::shared_ptr<gko::Array<IndexType>> first_row;
-    std::shared_ptr<gko::Array<IndexType>> permutation;
-    std::shared_ptr<gko::Array<IndexType>> i_permutation;
+    // index sets (host): global <-> local numbering, overlap rows, block starts, partition
+    // permutation and its inverse
+    using index_array = gko::Array<IndexType>;
+    std::shared_ptr<index_array> global_to_local, local_to_global, first_row, permutation,
+        i_permutation;
+    index_array overlap_row;
 };
 
 // Stage timer with the reference's bookkeeping (include/settings.hpp:508-523):
