@@ -300,13 +300,37 @@ def run_reference(args):
 # ----------------------------------------------------------------------------
 # B200 arm
 # ----------------------------------------------------------------------------
+class StdoutToStderr:
+    """Everything written to file descriptor 1 while this is active - by Python, torch, NCCL (its
+    version banner) or any other library - goes to stderr, so that stdout carries exactly the one
+    JSON line of the contract, printed after leaving the context."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+        return False
+
+
 def main():
     args = parse()
     if args.impl == "reference":
         run_reference(args)
         return
+    with StdoutToStderr():
+        line = run_b200(args)
+    if line is not None:
+        print(line, flush=True)
 
-    # keep stdout to the one JSON line: NCCL's banner goes to stderr
+
+def run_b200(args):
+    # NCCL's banner goes to stderr (and so does anything else that prints, see StdoutToStderr)
     os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     import torch
     import torch.distributed as dist
@@ -563,7 +587,9 @@ def main():
                "global_resnorm": res["global_resnorm"], "impl": "b200"}
         if tts is not None:
             out["time_to_solution"] = tts
-        print(json.dumps(out))
+        line = json.dumps(out)
+    else:
+        line = None
 
     for s in subs:
         s.close()
@@ -572,6 +598,7 @@ def main():
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    return line
 
 
 if __name__ == "__main__":
