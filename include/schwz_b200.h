@@ -204,6 +204,11 @@ int schwz_b200_read_mtx(const char *path, int32_t *n_rows, int64_t *nnz,
                         int32_t **rowptr, int32_t **col, double **val);  /* free with schwz_b200_host_free */
 void schwz_b200_host_free(void *p);
 int schwz_b200_partition_regular2d(int64_t N, int32_t P, uint32_t *part);
+/* px x py rectangular extension of PartitionRegular2D (include/partition_tools.hpp:70-94) for
+ * subdomain counts that are not perfect squares (8 -> 2 x 4); px = py = 0 picks the most square
+ * factorisation.  Identical to the rule above for perfect squares. */
+int schwz_b200_partition_regular2d_rect(int64_t N, int32_t P, int32_t px, int32_t py,
+                                        uint32_t *part);
 int schwz_b200_partition_metis(int32_t N, const int32_t *rowptr, const int32_t *col,
                                int32_t P, const char *objtype, uint32_t *part);
 

@@ -93,6 +93,12 @@ def max_threads():
     return int(lib().orc_max_threads())
 
 
+def set_rank_threads(n):
+    """Subdomains stepped side by side by Problem.step() (synchronous mode): 1 = one after the
+    other with the whole OpenMP team each; n > 1 = n at once with set_threads() threads each."""
+    lib().orc_set_rank_threads(int(n))
+
+
 def laplacian2d(n):
     """source/initialization.cpp:214-265 -> (rowptr, col, val) int32/int32/f64."""
     N = n * n
@@ -115,6 +121,16 @@ def laplacian3d(n):
 def partition_regular2d(N, P):
     pi = np.zeros(N, np.uint32)
     lib().orc_partition_regular2d(C.c_int64(N), C.c_int(P), _p(pi))
+    return pi
+
+
+def partition_regular2d_rect(N, P, px=0, py=0):
+    """px x py rectangular extension of regular2d (0, 0: most square factorisation, px <= py);
+    equals partition_regular2d for perfect-square P."""
+    pi = np.zeros(N, np.uint32)
+    if lib().orc_partition_regular2d_rect(C.c_int64(N), C.c_int(P), C.c_int(px), C.c_int(py),
+                                          _p(pi)) != 0:
+        raise ValueError("regular2d: N must be a square and px * py == P")
     return pi
 
 

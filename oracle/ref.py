@@ -187,6 +187,13 @@ class Run:
     def iter_count(self, r):
         return int(lib().ref_iter_count(self.h, C.c_int(r)))
 
+    def run_seconds(self, r=0):
+        """wall time of SolverRAS::run on rank r (the loop of source/schwarz_base.cpp:384-455
+        plus, when it converged, the final residual computation)"""
+        f = lib().ref_run_seconds
+        f.restype = C.c_double
+        return float(f(self.h, C.c_int(r)))
+
     def num_iterates(self, r):
         return int(lib().ref_num_iterates(self.h, C.c_int(r)))
 

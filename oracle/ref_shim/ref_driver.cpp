@@ -6,6 +6,7 @@
 // CUDA path. It mirrors what benchmarking/bench_ras.cpp:47-169 does with its flags.
 // TEST INFRASTRUCTURE; never part of the product.
 #include <cstdint>
+#include <chrono>
 #include <cstring>
 #include <iostream>
 #include <memory>
@@ -64,6 +65,7 @@ struct RankOut {
     std::vector<std::vector<IT>> get_lists, put_lists;
     std::vector<VT> local_rhs;
     int32_t iter_count = 0;
+    double run_seconds = 0.0;   // wall time of SolverRAS::run on this rank
     std::vector<VT> local_res, local_conv_res;
     std::vector<std::vector<VT>> global_res;
     std::vector<std::vector<VT>> iterates;
@@ -225,7 +227,10 @@ void rank_body(int rank, Run &run)
     solver.initialize();
     solver.harvest_setup();
     if (c.run) {
+        const auto t_run = std::chrono::steady_clock::now();
         solver.run(solution);
+        out.run_seconds =
+            std::chrono::duration<double>(std::chrono::steady_clock::now() - t_run).count();
         solver.harvest_run();
         if (rank == 0 && solution)
             out.solution.assign(solution->get_const_values(),
@@ -368,6 +373,7 @@ int ref_global_residuals(void *h, int rank, int j, double *out, int64_t cap)
     if (j >= static_cast<int>(g.size())) return 0;
     return copy_out(g[j], out, cap);
 }
+double ref_run_seconds(void *h, int rank) { return static_cast<Run *>(h)->ranks[rank].run_seconds; }
 int ref_iter_count(void *h, int rank) { return static_cast<Run *>(h)->ranks[rank].iter_count; }
 int ref_num_iterates(void *h, int rank)
 {

@@ -209,6 +209,37 @@ void partition_regular2d(int64_t N, int P, uint32_t *pi)
     }
 }
 
+// Rectangular extension of the rule above (NOT in the reference, whose sqrt truncation leaves
+// subdomains without rows unless P is a perfect square): the
+// n x n grid is cut into px block-rows x py block-columns, px * py == P, subdomain id =
+// py * j1 + j2 exactly as include/partition_tools.hpp:84 numbers them, block-row j1 = grid rows
+// [j1*n/px, (j1+1)*n/px), block-column j2 = grid columns [j2*n/py, (j2+1)*n/py) (integer
+// division: every row gets an owner when n is not divisible).  px = py = 0 picks the most
+// square factorisation with px <= py (8 -> 2 x 4, 4 -> 2 x 2, 64 -> 8 x 8).  For a perfect
+// square P and n divisible by sqrt(P) it reproduces partition_regular2d bit for bit.
+void regular2d_factors(int P, int &px, int &py)
+{
+    if (px > 0 && py > 0) return;
+    px = 1;
+    for (int d = 1; (int64_t)d * d <= P; ++d)
+        if (P % d == 0) px = d;
+    py = P / px;
+}
+
+int partition_regular2d_rect(int64_t N, int P, int px, int py, uint32_t *pi)
+{
+    const int64_t n = (int64_t)std::llround(std::sqrt((double)N));
+    if (n * n != N) return -1;
+    regular2d_factors(P, px, py);
+    if ((int64_t)px * py != P || px > n || py > n) return -1;
+    for (int j1 = 0; j1 < px; ++j1)
+        for (int64_t r = j1 * n / px; r < (j1 + 1) * n / px; ++r)
+            for (int j2 = 0; j2 < py; ++j2)
+                for (int64_t c = j2 * n / py; c < (j2 + 1) * n / py; ++c)
+                    pi[r * n + c] = (uint32_t)(py * j1 + j2);
+    return 0;
+}
+
 // -----------------------------------------------------------------------------
 // Per-subdomain ("rank") state.
 // -----------------------------------------------------------------------------
@@ -1547,6 +1578,22 @@ void local_to_global_vector(Problem &pb, int me)
 // source/schwarz_base.cpp:387-452, for all subdomains.  Returns the number of
 // ranks that left the loop in this pass (break at :432-433).
 // -----------------------------------------------------------------------------
+// Rank-parallel stepping (bench.py's CPU arm): the reference runs its P MPI ranks side by side,
+// each with its OpenMP team.  With g_rank_threads > 1 the per-rank stages of a synchronous
+// step run on that many host threads at once (nested teams of g_threads inside); every rank's
+// arithmetic is the same sequence as in the serial sweep, so the iterates do not change.
+int g_rank_threads = 1;
+template <class F>
+void for_ranks(int P, F f)
+{
+    if (g_rank_threads > 1) {
+#pragma omp parallel for num_threads(g_rank_threads) schedule(static, 1)
+        for (int p = 0; p < P; ++p) f(p);
+    } else {
+        for (int p = 0; p < P; ++p) f(p);
+    }
+}
+
 int ras_step(Problem &pb)
 {
     const int P = pb.P;
@@ -1555,16 +1602,15 @@ int ras_step(Problem &pb)
     if (!o.enable_onesided) {
         // synchronous: every stage completes on all ranks before the next
         exchange_twosided(pb);
-        for (int p = 0; p < P; ++p)
-            if (!pb.ranks[p].finished) update_boundary(pb, p);
         // local norms first (the allgather needs all of them)
         std::vector<int> loc(P, 0);
-        for (int p = 0; p < P; ++p) {
-            if (pb.ranks[p].finished) continue;
-            Rank &R = pb.ranks[p];
+        for_ranks(P, [&](int p) {
+            if (pb.ranks[p].finished) return;
+            update_boundary(pb, p);
             loc[p] = check_local_convergence(pb, p) ? 1 : 0;
-            R.res_hist.push_back(R.resnorm);
-        }
+        });
+        for (int p = 0; p < P; ++p)
+            if (!pb.ranks[p].finished) pb.ranks[p].res_hist.push_back(pb.ranks[p].resnorm);
         for (int p = 0; p < P; ++p) {
             if (pb.ranks[p].finished) continue;
             Rank &R = pb.ranks[p];
@@ -1590,11 +1636,11 @@ int ras_step(Problem &pb)
                 ++newly_finished;
             }
         }
-        for (int p = 0; p < P; ++p) {
-            if (pb.ranks[p].finished) continue;
+        for_ranks(P, [&](int p) {
+            if (pb.ranks[p].finished) return;
             local_solve(pb, p);
             local_to_global_vector(pb, p);
-        }
+        });
     } else {
         // asynchronous emulation: ranks run their whole loop body in turn
         for (int p = 0; p < P; ++p) {
@@ -1645,6 +1691,15 @@ void final_residual(Problem &pb, double *x_out, double out[4])
 extern "C" {
 
 void orc_set_threads(int n) { g_threads = n < 1 ? 1 : n; }
+// subdomains stepped side by side (1 = one after the other, each with the whole team)
+void orc_set_rank_threads(int n)
+{
+    g_rank_threads = n < 1 ? 1 : n;
+#ifdef _OPENMP
+    omp_set_dynamic(0);
+    omp_set_max_active_levels(g_rank_threads > 1 ? 2 : 1);
+#endif
+}
 int orc_max_threads()
 {
 #ifdef _OPENMP
@@ -1671,6 +1726,11 @@ int64_t orc_laplacian3d(int n, idx *rp, idx *ci, double *v)
     std::copy(A.v.begin(), A.v.end(), v);
     return A.nnz();
 }
+int orc_partition_regular2d_rect(int64_t N, int P, int px, int py, uint32_t *pi)
+{
+    return partition_regular2d_rect(N, P, px, py, pi);
+}
+
 void orc_partition_regular2d(int64_t N, int P, uint32_t *pi)
 {
     std::fill(pi, pi + N, 0u);  // resize()-zeroed, initialization.cpp:285

@@ -545,6 +545,14 @@ int schwz_b200_partition_regular2d(int64_t N, int32_t P, uint32_t *part)
     partition_regular2d(N, P, part);
     ABI_END
 }
+int schwz_b200_partition_regular2d_rect(int64_t N, int32_t P, int32_t px, int32_t py,
+                                        uint32_t *part)
+{
+    ABI_BEGIN
+    SCHWZ_REQUIRE(partition_regular2d_rect(N, P, px, py, part),
+                  "regular2d: N must be a square number and px * py == P");
+    ABI_END
+}
 int schwz_b200_partition_metis(int32_t N, const int32_t *rp, const int32_t *ci, int32_t P,
                                const char *objtype, uint32_t *part)
 {

@@ -239,6 +239,35 @@ void partition_regular2d(int64_t N, int32_t P, uint32_t *part)
         }
 }
 
+// px x py blocks of an n x n grid: the rectangular extension of the rule above for subdomain
+// counts that are not perfect squares (there the reference's truncating sqrt leaves subdomains
+// without rows; BASELINE.json configs[1] asks for a 2-D partition of 8 subdomains).
+// Same numbering as include/partition_tools.hpp:84 (id = py * block_row + block_column); cuts
+// at k*n/px and k*n/py.  px = py = 0: most square factorisation with px <= py.
+bool partition_regular2d_rect(int64_t N, int32_t P, int32_t px, int32_t py, uint32_t *part)
+{
+    int64_t n = (int64_t)std::sqrt((double)N);
+    while (n * n < N) ++n;
+    while (n * n > N) --n;
+    if (n * n != N || P < 1) return false;
+    if (px <= 0 || py <= 0) {
+        px = 1;
+        for (int32_t d = 2; (int64_t)d * d <= P; ++d)
+            if (P % d == 0) px = d;
+        py = P / px;
+    }
+    if ((int64_t)px * py != P || px > n || py > n) return false;
+    std::vector<int32_t> col_owner((size_t)n);
+    for (int32_t j2 = 0; j2 < py; ++j2)
+        for (int64_t c = j2 * n / py; c < (j2 + 1) * n / py; ++c) col_owner[c] = j2;
+    for (int32_t j1 = 0; j1 < px; ++j1)
+        for (int64_t r = j1 * n / px; r < (j1 + 1) * n / px; ++r) {
+            uint32_t *row = part + r * n;
+            for (int64_t c = 0; c < n; ++c) row[c] = (uint32_t)(py * j1 + col_owner[c]);
+        }
+    return true;
+}
+
 // -----------------------------------------------------------------------------
 // METIS (static library shipped inside the CUDA toolkit; idx_t = int64,
 // real_t = float — SURVEY F4).  Same call sequence as

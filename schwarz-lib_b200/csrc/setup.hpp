@@ -40,6 +40,7 @@ HostCsr materialize(const RowSource &src);
 HostCsr read_mtx(const std::string &path);   // gko::read + sort_by_column_index
 
 void partition_regular2d(int64_t N, int32_t P, uint32_t *part);
+bool partition_regular2d_rect(int64_t N, int32_t P, int32_t px, int32_t py, uint32_t *part);
 int partition_metis(int32_t N, const int32_t *rp, const int32_t *ci, int32_t P,
                     const char *objtype, uint32_t *part);
 int nd_ordering(int32_t n, const int32_t *rp, const int32_t *ci, int32_t *perm);

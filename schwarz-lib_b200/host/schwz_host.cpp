@@ -179,9 +179,21 @@ void Initialize<V, I>::partition(const Settings &settings, const Metadata<V, I> 
         SAY(" Regular 1D partition");
     } else if (kind == Settings::partition_regular2d) {
         SAY(" Regular 2D partition");
-        B200_CHECK(schwz_b200_partition_regular2d((int64_t)metadata.global_size,
-                                                  (int32_t)metadata.num_subdomains,
-                                                  partition_indices.data()));
+        // perfect-square subdomain counts: the reference's rule, literally
+        // (include/partition_tools.hpp:70-94).  Otherwise that rule leaves subdomains without
+        // rows (its sqrt truncates), so the px x py extension takes over (8 -> 2 x 4).
+        const int32_t Pn = (int32_t)metadata.num_subdomains;
+        int32_t sq = (int32_t)std::sqrt((double)Pn);
+        while (sq * sq > Pn) --sq;
+        while ((sq + 1) * (sq + 1) <= Pn) ++sq;
+        if (sq * sq == Pn) {
+            B200_CHECK(schwz_b200_partition_regular2d((int64_t)metadata.global_size, Pn,
+                                                      partition_indices.data()));
+        } else {
+            SAY(" (subdomain count is not a perfect square: px x py extension)");
+            B200_CHECK(schwz_b200_partition_regular2d_rect((int64_t)metadata.global_size, Pn, 0,
+                                                           0, partition_indices.data()));
+        }
         if (settings.write_debug_out) {
             std::ofstream file("part_indices.csv");
             file << "idx,subd\n";

@@ -160,6 +160,14 @@ def partition_regular2d(N, P):
     return part
 
 
+def partition_regular2d_rect(N, P, px=0, py=0):
+    """px x py rectangular extension of regular2d (0, 0: most square factorisation)"""
+    part = np.zeros(N, np.uint32)
+    _chk(load().schwz_b200_partition_regular2d_rect(C.c_int64(N), C.c_int32(P), C.c_int32(px),
+                                                    C.c_int32(py), _p(part)))
+    return part
+
+
 def partition_metis(rp, ci, P, objtype="null"):
     rp, ci = _i32(rp), _i32(ci)
     N = len(rp) - 1

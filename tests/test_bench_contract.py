@@ -29,10 +29,41 @@ def test_reference_arm_prints_the_contract_line():
     assert d["dtype"] == "f64" and d["data"] == "synthetic" and d["vs_baseline"] is None
     assert "workload" in d["config"] and "model" not in d["config"]
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
+    # up to 2048^2 the reference's own loop (oracle/_ref) is what is timed
+    assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1
+    assert cb["value"] == d["value"] and cb["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0,
                         "d2h_bytes_per_step": 0}
     assert d["gpu_launches"] == 0
+
+
+def test_reference_arm_steps_the_real_loop_with_every_core_under_torchrun():
+    """torchrun exports OMP_NUM_THREADS=1 to its workers: the arm sizes its team from the CPU
+    affinity mask instead, really runs every requested step of the oracle's outer loop (no
+    extrapolation), and never loads the product library."""
+    code = (
+        "import os, sys, json, io, contextlib\n"
+        "sys.argv = ['bench.py', '--impl', 'reference', '--size', '2560', '--steps', '3', '--warmup', '2']\n"
+        "sys.path.insert(0, %r)\n"
+        "import bench\n"
+        "buf = io.StringIO()\n"
+        "with contextlib.redirect_stdout(buf):\n"
+        "    bench.main()\n"
+        "d = json.loads(buf.getvalue())\n"
+        "maps = open('/proc/self/maps').read()\n"
+        "d['_product_loaded'] = 'libschwz_b200' in maps or 'schwz_b200' in sys.modules\n"
+        "d['_oracle_loaded'] = 'libschwz_oracle' in maps\n"
+        "print(json.dumps(d))\n" % ROOT)
+    e = dict(os.environ)
+    e["OMP_NUM_THREADS"] = "1"
+    p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=900,
+                       env=e, cwd=ROOT)
+    assert p.returncode == 0, p.stderr[-2000:]
+    d = json.loads(p.stdout.strip().splitlines()[-1])
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] == len(os.sched_getaffinity(0))
+    assert d["steps"] == 3 and "3 outer iteration(s) of the oracle's own RAS loop" in cb["sample"]
+    assert d["_oracle_loaded"] and not d["_product_loaded"]
 
 
 def test_reference_arm_other_ranks_stay_silent():
