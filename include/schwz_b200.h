@@ -327,6 +327,11 @@ int schwz_b200_ras_connect_conv(schwz_ras *r, int32_t peer_rank, void *peer_mail
  * (source/restricted_schwarz.cpp:753-851): 0 Put gathered (also the synchronous
  * exchange), 1 Get gathered, 2 Put one-by-one, 3 Get one-by-one. */
 int schwz_b200_ras_set_exchange_mode(schwz_ras *r, int32_t mode);
+/* 1: one-sided semantics for the Put-gathered exchange (comm_settings.enable_onesided,
+ * source/restricted_schwarz.cpp:715-852): a single receive buffer, no epoch flags, the receiver
+ * scatters whatever it holds; stale values of a run before schwz_b200_ras_reset are cleared.
+ * 0 (default): synchronous epochs (double-buffered, flag per in-neighbour). */
+int schwz_b200_ras_set_onesided(schwz_ras *r, int32_t onesided);
 /* connects every pair of subdomains living in this process (out, in and conv) */
 int schwz_b200_ras_connect_local(schwz_ras **subdomains, int32_t n_local, schwz_setup *s);
 /* loop stages (asynchronous on the subdomain's stream) */
@@ -394,6 +399,11 @@ typedef struct {
     schwz_comm *comm;
 } schwz_loop_options;
 
+/* The loop runs ahead of the host: stages are enqueued a few outer iterations deep, the
+ * convergence decision is taken on the device and turns whatever was enqueued past the break
+ * point into no-ops; the host looks at the loop state once per chunk of iterations
+ * (SCHWZ_B200_OUTER_CHUNK, default 4).  A halo wait that exceeds SCHWZ_B200_HALO_TIMEOUT_MS
+ * (default 20000) makes the call fail with "halo exchange timed out". */
 typedef struct {
     int32_t iters;                 /* metadata.iter_count at exit */
     int32_t converged;
@@ -404,6 +414,12 @@ typedef struct {
 int schwz_b200_ras_run(schwz_ras **subdomains, int32_t n_local,
                        const schwz_loop_options *opt, schwz_loop_result *res,
                        double *host_resnorm_history /* max_iters*n_local or NULL */);
+
+/* One synchronous halo exchange outside the loop (collective over all processes): afterwards
+ * the overlap / halo entries of every x hold the neighbours' current values - what the final
+ * residual of Solve::compute_residual_norm (source/solve.cpp:1025-1085) needs when the loop
+ * ended on its iteration budget. */
+int schwz_b200_ras_refresh_halo(schwz_ras **subdomains, int32_t n_local, int32_t num_subdomains);
 
 /* ---- NCCL communicator for the residual-norm allgather ----------------------
  * replaces: MPI_Allgather (source/solve.cpp:890-891).  id128 is an

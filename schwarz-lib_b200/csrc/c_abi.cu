@@ -72,6 +72,8 @@ int schwz_b200_ctx_create(int device, schwz_ctx **out)
     g_use_small_solvers = !(ns && ns[0] == '1');
     const char *ng = std::getenv("SCHWZ_B200_NO_CG_GRAPH");
     g_use_cg_graph = !(ng && ng[0] == '1');
+    const char *ht = std::getenv("SCHWZ_B200_HALO_TIMEOUT_MS");
+    if (ht && std::atoll(ht) > 0) g_halo_timeout_ns = std::atoll(ht) * 1000000ll;
     *out = new schwz_ctx(device);
     ABI_END
 }
@@ -816,6 +818,12 @@ int schwz_b200_ras_set_exchange_mode(schwz_ras *r, int32_t mode)
     r->impl->set_exchange_mode(mode);
     ABI_END
 }
+int schwz_b200_ras_set_onesided(schwz_ras *r, int32_t onesided)
+{
+    ABI_BEGIN
+    r->impl->set_onesided(onesided != 0);
+    ABI_END
+}
 int schwz_b200_ras_connect_local(schwz_ras **subs, int32_t n, schwz_setup *s)
 {
     ABI_BEGIN
@@ -875,10 +883,17 @@ int schwz_b200_ras_local_residual(schwz_ras *r)
 int schwz_b200_ras_residual_norm(schwz_ras *r, double *out)
 {
     ABI_BEGIN
+    // the stage-by-stage caller's one synchronisation per outer iteration: the halo wait's error
+    // word comes back with the norm (a lost peer must not go unnoticed)
     r->impl->ctx.use();
+    int32_t err = 0;
     SCHWZ_CUDA(cudaMemcpyAsync(out, r->impl->resnorm_dev, 8, cudaMemcpyDeviceToHost,
                                r->impl->ctx.stream));
+    SCHWZ_CUDA(cudaMemcpyAsync(&err, r->impl->err_word(), 4, cudaMemcpyDeviceToHost,
+                               r->impl->ctx.stream));
     r->impl->ctx.sync();
+    SCHWZ_REQUIRE(err == 0, "halo exchange timed out: a neighbour's boundary values did not "
+                            "arrive within SCHWZ_B200_HALO_TIMEOUT_MS");
     ABI_END
 }
 int schwz_b200_ras_residual_norm_dev(schwz_ras *r, double **dev)
@@ -934,7 +949,9 @@ int schwz_b200_ras_get_local_solution(schwz_ras *r, double *out)
     ABI_BEGIN
     Ras &R = *r->impl;
     R.ctx.use();
-    SCHWZ_CUDA(cudaMemcpyAsync(out, R.local_sol, sizeof(double) * (size_t)R.local_size_x,
+    // after an iterative local solve local_solution == init_guess (source/solve.cpp:781); the
+    // copy is not materialised on the device
+    SCHWZ_CUDA(cudaMemcpyAsync(out, R.solution_vector(), sizeof(double) * (size_t)R.local_size_x,
                                cudaMemcpyDeviceToHost, R.ctx.stream));
     R.ctx.sync();
     ABI_END
@@ -1056,6 +1073,15 @@ int schwz_b200_ras_run(schwz_ras **subs, int32_t n_local, const schwz_loop_optio
     res->global_resnorm = lr.global_resnorm;
     res->global_resnorm0 = lr.global_resnorm0;
     res->elapsed_s = lr.elapsed_s;
+    ABI_END
+}
+
+int schwz_b200_ras_refresh_halo(schwz_ras **subs, int32_t n_local, int32_t num_subdomains)
+{
+    ABI_BEGIN
+    std::vector<Ras *> v;
+    for (int32_t i = 0; i < n_local; ++i) v.push_back(subs[i]->impl.get());
+    ras_refresh_halo(v, num_subdomains);
     ABI_END
 }
 

@@ -45,9 +45,8 @@ inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_
 constexpr int kBlock = 256;       // threads per CTA for every kernel here
 constexpr int kSpmvUnroll = 8;    // nnz per thread per CTA tile
 constexpr int kSpmvTile = kBlock * kSpmvUnroll;   // nnz staged per CTA
-constexpr int kNumSMs = 148;      // B200
 constexpr int kVecCtasPerSM = 8;  // resident CTAs/SM targeted by vector kernels
-constexpr int kVecGrid = kNumSMs * kVecCtasPerSM;
+// (grids are sized from the SM count the device reports: Ctx::num_sms, 148 on B200)
 constexpr int kMaxPartials = 65536;
 
 #ifdef __CUDACC__
@@ -120,6 +119,12 @@ __device__ __forceinline__ int ld_relaxed_sys_i32(const int *p)
     int v;
     asm volatile("ld.relaxed.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
+}
+__device__ __forceinline__ unsigned long long global_timer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
 }
 #endif  // __CUDACC__
 

@@ -12,6 +12,8 @@ namespace schwz_b200 {
 
 struct Ctx {
     int device = 0;
+    int num_sms = 148;                 // queried at creation (B200: 148)
+    int vec_grid() const { return num_sms * kVecCtasPerSM; }
     cudaStream_t stream = nullptr;
     double *partials = nullptr;        // kMaxPartials doubles
     unsigned int *tickets = nullptr;   // 16 tickets, zero-initialised
@@ -100,20 +102,23 @@ void launch_dot(const Ctx &ctx, int64_t n, const double *a, const double *b, dou
                 bool sqrt_result);
 void launch_axpy(const Ctx &ctx, int64_t n, double alpha, const double *x, double *y);
 void launch_copy(const Ctx &ctx, int64_t n, const double *src, double *dst);
+// dst = src as a kernel that honours a device stop flag (no-op when *stop != 0)
+void launch_copy_guarded(const Ctx &ctx, int64_t n, const double *src, double *dst,
+                         const int32_t *stop);
 void launch_gather(const Ctx &ctx, int32_t n, const int32_t *idx, const double *from,
                    double *into, int op);
 void launch_scatter(const Ctx &ctx, int32_t n, const int32_t *idx, const double *from,
                     double *into, int op);
 void launch_permute(const Ctx &ctx, int32_t n, const int32_t *perm, int inverse,
-                    const double *in, double *out);
+                    const double *in, double *out, const int32_t *stop = nullptr);
 
 // CG step kernels (Ginkgo Cg semantics)
 void launch_cg_init(const Ctx &ctx, CgScalars *s, int32_t max_iters, double tol,
-                    const int32_t *outer_stop);
+                    const int32_t *outer_stop, cudaGraphConditionalHandle loop = 0);
 void launch_cg_xp_update(const Ctx &ctx, int64_t n, const double *r_or_z, double *p, double *x,
                          const CgScalars *s);
 void launch_cg_r_update(const Ctx &ctx, int64_t n, double *r, const double *q, CgScalars *s,
-                        bool precond = false);
+                        bool precond = false, cudaGraphConditionalHandle loop = 0);
 void launch_cg_flush_x(const Ctx &ctx, int64_t n, double *x, const double *p, const CgScalars *s);
 
 // halo
@@ -121,16 +126,50 @@ void launch_halo_pack_push(const Ctx &ctx, int32_t nseg, const int32_t *seg_off_
                            int32_t total, const int32_t *src_idx, const double *x,
                            void *const *dst_ptrs, unsigned long long *const *flag_ptrs,
                            unsigned long long epoch, const int32_t *stop, bool f32 = false);
+// flags != nullptr: wait (bounded by timeout_ns) until every in-neighbour has published `epoch`;
+// on expiry *error_flag = 1 (the host raises at its next poll).  stop: no-op when set.
 void launch_halo_unpack(const Ctx &ctx, int32_t nseg, int32_t total, const int32_t *dst_idx,
                         const void *recv, double *x, const unsigned long long *flags,
-                        unsigned long long epoch, int32_t *error_flag, bool f32 = false);
+                        unsigned long long epoch, int32_t *error_flag, bool f32 = false,
+                        const int32_t *stop = nullptr);
+extern long long g_halo_timeout_ns;   // SCHWZ_B200_HALO_TIMEOUT_MS, default 20 s
 
 void launch_halo_put_elements(const Ctx &ctx, int32_t nseg, const int32_t *seg_off_dev,
                               int32_t total, const int32_t *src_idx, const int32_t *remote_slot,
-                              const double *x, double *const *peer_x);
+                              const double *x, double *const *peer_x,
+                              const int32_t *stop = nullptr);
 void launch_halo_pull(const Ctx &ctx, int32_t nseg, const int32_t *seg_off_dev, int32_t total,
                       const int32_t *dst_idx, const int32_t *src_idx,
-                      const void *const *src_ptrs, double *x, bool f32 = false);
+                      const void *const *src_ptrs, double *x, bool f32 = false,
+                      const int32_t *stop = nullptr);
+
+// Device-resident bookkeeping of one subdomain's outer loop (what Solve::check_convergence keeps
+// in host variables, source/solve.cpp:796-1005).  `stop` is the flag every launch of the
+// subdomain honours: once set (converged, or an error) the rest of the enqueued work is no-ops,
+// so the host never has to read anything back inside the loop.
+struct OuterState {
+    double resnorm, resnorm0, gres, gres0;
+    int32_t num_converged, stop, finished_iter, iter;
+    int32_t error;   // 0 ok, 1 halo wait timed out, 2 residual norm is NaN, 3 diverged
+    int32_t pad[3];
+};
+enum OuterError { OUTER_OK = 0, OUTER_HALO_TIMEOUT = 1, OUTER_NAN = 2, OUTER_DIVERGED = 3 };
+
+// out[i] = *norm_ptrs[i]: the local residual norms of a process, contiguous for the allgather
+void launch_gather_norms(const Ctx &ctx, int32_t n, const double *const *norm_ptrs, double *out);
+// Synchronous global decision (source/solve.cpp:888-912 + the break test of
+// schwarz_base.cpp:432-433) for the nl subdomains of this process: all[P] = every subdomain's
+// local residual norm in rank order, slot[i] = position of local subdomain i in it.
+void launch_ras_decide(const Ctx &ctx, int32_t P, int32_t nl, const double *all,
+                       const int32_t *slot, OuterState *const *states, double tol,
+                       int32_t check, int32_t enable_global_check, int32_t iter, double *history);
+// One-sided: local ratio test + flag protocol + break test on the subdomain's own stream
+// (source/solve.cpp:913-943).  protocol: 0 flag flooding, 1 tree, 2 accumulate.
+void launch_ras_conv_decide(const Ctx &ctx, int32_t protocol, int32_t P, int32_t me,
+                            OuterState *state, const double *resnorm_dev, double tol,
+                            int32_t check, int32_t iter, double *history, int32_t *conv,
+                            int32_t *conv_sent, int32_t n_out, int32_t *const *out_conv,
+                            int32_t *const *peer_conv, int32_t *num_converged);
 
 // convergence flags (include/conv_tools.hpp:248-274 on peer-mapped words)
 void launch_conv_forward(const Ctx &ctx, int32_t P, int32_t me, int32_t converged_all_local,

@@ -7,6 +7,7 @@
 #include <chrono>
 #include <cmath>
 #include <cfloat>
+#include <cstdlib>
 #include <cstring>
 
 #include "engine.hpp"
@@ -147,6 +148,15 @@ Ras::Ras(const Ctx &ctx_, Setup &setup, int32_t rank_, const double *host_rhs_gl
     init_guess = ctx.alloc_zero<double>(local_size_x);
     work = ctx.alloc_zero<double>(2 * (size_t)local_size_x);
     resnorm_dev = ctx.alloc_zero<double>(2);
+    state = (OuterState *)ctx.alloc_zero<char>(sizeof(OuterState));
+    {
+        OuterState init{};
+        init.resnorm = init.resnorm0 = init.gres0 = -1.0;
+        init.finished_iter = -1;
+        SCHWZ_CUDA(cudaMemcpyAsync(state, &init, sizeof(init), cudaMemcpyHostToDevice, ctx.stream));
+        SCHWZ_CUDA(cudaStreamSynchronize(ctx.stream));
+    }
+    SCHWZ_CUDA(cudaEventCreateWithFlags(&ev_resid, cudaEventDisableTiming));
     num_converged_dev = ctx.alloc_zero<int32_t>(2);
     conv_sent = ctx.alloc_zero<int32_t>(std::max(P, 3));
 
@@ -250,7 +260,9 @@ Ras::~Ras()
                     (void *)in_send_dev_, (void *)in_x_dev_, (void *)out_x_dev_,
                     (void *)send_seg_dev_, (void *)conv_peer_dev_})
         ctx.release(p);
-    for (void *p : {(void *)local_rhs, (void *)local_sol, (void *)init_guess,
+    hub.reset();
+    if (ev_resid) cudaEventDestroy(ev_resid);
+    for (void *p : {(void *)local_rhs, (void *)local_sol, (void *)init_guess, (void *)state,
                     (void *)work, (void *)resnorm_dev, (void *)num_converged_dev,
                     (void *)conv_sent, (void *)mailbox, (void *)in_dst_, (void *)out_src_,
                     (void *)out_off_, (void *)out_dst_dev_[0], (void *)out_dst_dev_[1],
@@ -297,13 +309,51 @@ void Ras::reset_state()
     SCHWZ_CUDA(cudaMemsetAsync(init_guess, 0, sizeof(double) * (size_t)local_size_x, ctx.stream));
     SCHWZ_CUDA(cudaMemsetAsync(local_sol, 0, sizeof(double) * (size_t)local_size_x, ctx.stream));
     SCHWZ_CUDA(cudaMemsetAsync(conv(), 0, sizeof(int32_t) * (size_t)std::max(P, 3), ctx.stream));
+    SCHWZ_CUDA(cudaMemsetAsync(err_word(), 0, sizeof(int32_t), ctx.stream));
     SCHWZ_CUDA(cudaMemsetAsync(conv_sent, 0, sizeof(int32_t) * (size_t)std::max(P, 3), ctx.stream));
+    OuterState init{};
+    init.resnorm = init.resnorm0 = init.gres0 = -1.0;
+    init.finished_iter = -1;
+    SCHWZ_CUDA(cudaMemcpyAsync(state, &init, sizeof(init), cudaMemcpyHostToDevice, ctx.stream));
+    SCHWZ_CUDA(cudaStreamSynchronize(ctx.stream));   // `init` lives on this stack frame
     resnorm = resnorm0 = -1.0;
     gres = 0.0;
     gres0 = -1.0;
     num_converged = 0;
     finished = false;
     finished_iter = -1;
+    // The halo values of the previous run still sit in the receive / send buffers.  A
+    // synchronous run overwrites them before it reads them; a one-sided run would scatter them
+    // at its first exchange if the peers' fresh values have not landed yet, so it clears them
+    // on entry (not here: a peer process that has already started its next run may be writing
+    // into them by now - reset is not a collective).  The epoch counters keep counting.
+    recv_dirty_ = true;
+}
+
+void Ras::set_onesided(bool o)
+{
+    onesided_ = o;
+    if (o && recv_dirty_) {
+        ctx.use();
+        SCHWZ_CUDA(cudaMemsetAsync(mailbox, 0, (size_t)(2 * mbox.recv_stride), ctx.stream));
+        SCHWZ_CUDA(cudaMemsetAsync(mailbox + mbox.send_off, 0,
+                                   (size_t)(mbox.slots_off - mbox.send_off), ctx.stream));
+        recv_dirty_ = false;
+    }
+}
+
+void Ras::fetch_state(OuterState &out)
+{
+    ctx.use();
+    SCHWZ_CUDA(cudaMemcpyAsync(&out, state, sizeof(out), cudaMemcpyDeviceToHost, ctx.stream));
+    SCHWZ_CUDA(cudaStreamSynchronize(ctx.stream));
+    resnorm = out.resnorm;
+    resnorm0 = out.resnorm0;
+    gres = out.gres;
+    gres0 = out.gres0;
+    num_converged = out.num_converged;
+    finished = out.stop != 0 && out.error == OUTER_OK;
+    finished_iter = out.finished_iter;
 }
 
 float Ras::kernel_time_ms(int kind, int reps)
@@ -321,14 +371,14 @@ float Ras::kernel_time_ms(int kind, int reps)
             launch_spmv(ctx, *A, -1.0, x, 1.0, local_sol, q, EPI_NRM2, nullptr, resnorm_dev + 1,
                         local_size_x, nullptr);
             break;
+        // 4: push + unpack, 5 / 6: the two halves on their own.  Timing launches rewrite / reread
+        // the buffers of the last epoch: the counters do not move.
         case 4:
-            exchange_push(0);
-            exchange_unpack(0, false);
+            exchange_push(0, true);
+            exchange_unpack(0, false, false);
             break;
-        // 5 / 6: the two halves on their own (call both with the same reps so that the epoch
-        // counters of push and unpack end up in step again)
-        case 5: exchange_push(0); break;
-        case 6: exchange_unpack(0, false); break;
+        case 5: exchange_push(0, true); break;
+        case 6: exchange_unpack(0, false, false); break;
         default: SCHWZ_REQUIRE(cg != nullptr, "no CG solver on this subdomain"); cg->bench_step(kind, work);
         }
     };
@@ -469,26 +519,41 @@ void Ras::upload_peer_tables()
 // A8 send side: pack x[own] for every out-neighbour and store it into the
 // neighbours' receive buffers (epoch parity selects the buffer), publish the
 // epoch.  The flag store is always made: a same-process neighbour ignores it.
-void Ras::exchange_push(int32_t iter)
+void Ras::exchange_push(int32_t iter, bool repush)
 {
     upload_peer_tables();
     const int32_t no = (int32_t)nbr_out.size();
+    const int32_t *stop = stop_ptr();
+    // what travels is x[own]; right after a local solve that is solution_vector()[0..local_size)
+    // as well, but x is what every variant (and every caller of the stages) agrees on
     if (no > 0 && exchange_mode == EXCHANGE_PUT_GATHERED) {
-        // epochs count exchanges over the lifetime of the subdomain, so the
-        // loop may be entered repeatedly (warm-up + timed runs)
-        ++push_epoch_;
-        launch_halo_pack_push(ctx, no, out_off_, out_total_, out_src_, x,
-                              out_dst_dev_[push_epoch_ & 1], out_flag_dev_,
-                              (unsigned long long)push_epoch_, nullptr, opt.use_mixed_precision != 0);
+        if (onesided_) {
+            // one receive buffer, no flags: the receiver takes whatever is there (:789-799)
+            launch_halo_pack_push(ctx, no, out_off_, out_total_, out_src_, x, out_dst_dev_[0],
+                                  nullptr, 0, stop, opt.use_mixed_precision != 0);
+        } else {
+            // epochs count exchanges over the lifetime of the subdomain, so the
+            // loop may be entered repeatedly (warm-up + timed runs).  A push left over from
+            // the last ras_run (nobody has unpacked it) is rewritten, not followed by another.
+            if (tail_pending) {
+                repush = true;
+                tail_pending = false;
+            }
+            if (!repush || push_epoch_ == 0) ++push_epoch_;
+            launch_halo_pack_push(ctx, no, out_off_, out_total_, out_src_, x,
+                                  out_dst_dev_[push_epoch_ & 1], out_flag_dev_,
+                                  (unsigned long long)push_epoch_, stop,
+                                  opt.use_mixed_precision != 0);
+        }
     } else if (no > 0 && exchange_mode == EXCHANGE_GET_GATHERED) {
         // pack_buffer into my own send buffer; the receivers come and get it (:807-818)
         launch_halo_pack_push(ctx, no, out_off_, out_total_, out_src_, x, send_seg_dev_, nullptr, 0,
-                              nullptr, opt.use_mixed_precision != 0);
+                              stop, opt.use_mixed_precision != 0);
     } else if (no > 0 && exchange_mode == EXCHANGE_PUT_ONE_BY_ONE) {
         for (size_t j = 0; j < nbr_out.size(); ++j)
             SCHWZ_REQUIRE(out_x_host_[j] != nullptr, "out-neighbour not connected");
         launch_halo_put_elements(ctx, no, out_off_, out_total_, out_src_, out_remote_slot_, x,
-                                 out_x_dev_);
+                                 out_x_dev_, stop);
     }
     SCHWZ_CUDA(cudaEventRecord(ev_pushed, ctx.stream));
     last_push_iter = iter;
@@ -502,12 +567,13 @@ void Ras::wait_push_of(const Ras &nbr)
 
 // A8 receive side: scatter the receive buffer of this epoch into the
 // overlap + halo slots of x.
-void Ras::exchange_unpack(int32_t iter, bool wait_flags)
+void Ras::exchange_unpack(int32_t iter, bool wait_flags, bool advance)
 {
     const int32_t ni = (int32_t)nbr_in.size();
-    if (ni == 0) return;
+    const int32_t *stop = stop_ptr();
     if (exchange_mode != EXCHANGE_PUT_GATHERED) {
         SCHWZ_REQUIRE(!wait_flags, "only the Put-gathered exchange has a synchronous mode");
+        if (ni == 0) return;
         upload_peer_tables();
         if (exchange_mode == EXCHANGE_PUT_ONE_BY_ONE) return;   // the Put was the update
         const bool gathered = exchange_mode == EXCHANGE_GET_GATHERED;
@@ -517,27 +583,39 @@ void Ras::exchange_unpack(int32_t iter, bool wait_flags)
         // one-by-one moves ValueType elements of x itself: no float mirror (comm_helpers.hpp:58-89)
         launch_halo_pull(ctx, ni, in_off_, in_total_, in_dst_, gathered ? nullptr : in_remote_idx_,
                          gathered ? in_send_dev_ : in_x_dev_, x,
-                         gathered && opt.use_mixed_precision != 0);
+                         gathered && opt.use_mixed_precision != 0, stop);
         return;
     }
-    ++unpack_epoch_;
-    const void *recv = mailbox + (unpack_epoch_ & 1) * mbox.recv_stride;
+    if (onesided_) {
+        if (ni == 0) return;
+        launch_halo_unpack(ctx, ni, in_total_, in_dst_, mailbox, x, nullptr, 0, nullptr,
+                           opt.use_mixed_precision != 0, stop);
+        return;
+    }
+    const int64_t e = advance ? ++unpack_epoch_ : std::max<int64_t>(unpack_epoch_, 1);
+    if (ni == 0) return;
+    const void *recv = mailbox + (e & 1) * mbox.recv_stride;
     const unsigned long long *flags =
         wait_flags ? (const unsigned long long *)(mailbox + mbox.flags_off) : nullptr;
-    launch_halo_unpack(ctx, ni, in_total_, in_dst_, recv, x, flags,
-                       (unsigned long long)unpack_epoch_, err_word(), opt.use_mixed_precision != 0);
+    // a timed-out wait raises the error word of the loop state (read by the host at its next
+    // poll) and the mailbox's own error word (stage-by-stage callers: schwz_b200_ras_halo_error)
+    launch_halo_unpack(ctx, ni, in_total_, in_dst_, recv, x, flags, (unsigned long long)e,
+                       guarded_ ? &state->error : err_word(), opt.use_mixed_precision != 0, stop);
 }
 
 // A9: local_solution = local_rhs - I * x  (source/restricted_schwarz.cpp:992-1017)
 void Ras::update_boundary()
 {
-    launch_copy(ctx, local_size, local_rhs, local_sol);
+    const int32_t *stop = stop_ptr();
+    sol_in_guess_ = false;
+    launch_copy_guarded(ctx, local_size, local_rhs, local_sol, stop);
     if (overlap_size > 0) {
         if (P > 1 && opt.overlap > 0 && I->nnz > 0)
             launch_spmv(ctx, *I, -1.0, x, 1.0, local_rhs + local_size, local_sol + local_size,
-                        EPI_NONE, nullptr, nullptr, 0, nullptr);
+                        EPI_NONE, nullptr, nullptr, 0, stop);
         else
-            launch_copy(ctx, overlap_size, local_rhs + local_size, local_sol + local_size);
+            launch_copy_guarded(ctx, overlap_size, local_rhs + local_size, local_sol + local_size,
+                                stop);
     }
 }
 
@@ -547,32 +625,35 @@ void Ras::update_boundary()
 void Ras::local_residual()
 {
     launch_spmv(ctx, *A, -1.0, x, 1.0, local_sol, work, EPI_NRM2, nullptr, resnorm_dev,
-                local_size_x, nullptr);
+                local_size_x, stop_ptr());
 }
 
 // A12 / A13 (source/solve.cpp:709-781)
 void Ras::local_solve()
 {
+    const int32_t *stop = stop_ptr();
     if (opt.local_solver == 2) {
         const int32_t cap = opt.local_max_iters == -1 ? local_size_x : opt.local_max_iters;
-        if (opt.non_symmetric) gmres->solve(local_sol, init_guess, cap, opt.local_tol);
-        else cg->solve(local_sol, init_guess, cap, opt.local_tol);
-        // local_solution <- init_guess (:781) is folded into restrict_to_x,
-        // which reads init_guess directly; keep local_solution coherent for
-        // callers that inspect it
-        launch_copy(ctx, local_size_x, init_guess, local_sol);
+        if (opt.non_symmetric) gmres->solve(local_sol, init_guess, cap, opt.local_tol, stop);
+        else cg->solve(local_sol, init_guess, cap, opt.local_tol, stop);
+        sol_in_guess_ = true;
+        // local_solution <- init_guess (:781) is not materialised: restrict_to_x and the
+        // accessors read init_guess (solution_vector())
     } else {
         SCHWZ_REQUIRE(Ltrs && Utrs && fperm, "direct local solve without factors");
         double *perm_sol = work, *tmp = work + local_size_x;
-        launch_permute(ctx, local_size_x, fperm, 0, local_sol, perm_sol);
-        Ltrs->solve(perm_sol, tmp);
-        Utrs->solve(tmp, perm_sol);
-        launch_permute(ctx, local_size_x, fperm_col ? fperm_col : fperm, 1, perm_sol, local_sol);
+        launch_permute(ctx, local_size_x, fperm, 0, local_sol, perm_sol, stop);
+        Ltrs->solve(perm_sol, tmp, stop);
+        Utrs->solve(tmp, perm_sol, stop);
+        launch_permute(ctx, local_size_x, fperm_col ? fperm_col : fperm, 1, perm_sol, local_sol,
+                       stop);
     }
 }
 
+const double *Ras::solution_vector() const { return sol_in_guess_ ? init_guess : local_sol; }
+
 // A14: x[own] = local_solution[0 .. local_size)  (source/communicate.cpp:65-94)
-void Ras::restrict_to_x() { launch_copy(ctx, local_size, local_sol, x); }
+void Ras::restrict_to_x() { launch_copy_guarded(ctx, local_size, solution_vector(), x, stop_ptr()); }
 
 double Ras::true_residual_sq()
 {
@@ -605,6 +686,27 @@ void Ras::conv_accumulate(int32_t converged_all_local)
                            num_converged_dev);
 }
 
+// one-sided decision on the device: ratio test on the residual norm the SpMV left in
+// resnorm_dev, flag protocol, break test (source/solve.cpp:913-943)
+void Ras::conv_decide(int32_t protocol, double tol, int32_t check, int32_t iter,
+                      double *history_slot)
+{
+    upload_peer_tables();
+    if (protocol == 1) {
+        if (rank > 0) SCHWZ_REQUIRE(conv_peer_host_[(rank - 1) / 2] != nullptr, "tree parent not connected");
+        for (int32_t p = 2 * rank + 1; p <= 2 * rank + 2; ++p)
+            if (p < P) SCHWZ_REQUIRE(conv_peer_host_[p] != nullptr, "tree child not connected");
+    } else if (protocol == 2) {
+        for (int32_t q = 0; q < P; ++q)
+            SCHWZ_REQUIRE(conv_peer_host_[q] != nullptr,
+                          "accumulate convergence check: every subdomain's flags must be "
+                          "connected (schwz_b200_ras_connect_conv)");
+    }
+    launch_ras_conv_decide(ctx, protocol, P, rank, state, resnorm_dev, tol, check, iter,
+                           history_slot, conv(), conv_sent, (int32_t)nbr_out.size(), out_conv_dev_,
+                           conv_peer_dev_, num_converged_dev);
+}
+
 void Ras::conv_tree(int32_t converged_all_local)
 {
     upload_peer_tables();
@@ -615,13 +717,132 @@ void Ras::conv_tree(int32_t converged_all_local)
 }
 
 // =============================================================================
-// The outer loop over the subdomains of this process.  One host thread drives
-// all local subdomains stage by stage; every stage is asynchronous on the
-// subdomain's stream, and the only host synchronisation per outer iteration is
-// the read-back of the residual norms for the convergence decision — the same
-// point at which the reference copies its norm to the host
-// (source/solve.cpp:841-843).
+// The outer loop over the subdomains of this process.  One host thread ENQUEUES the stages of
+// all local subdomains, a few outer iterations ahead of the device; nothing is read back inside
+// an iteration.  The convergence decision is taken on the device (ras_decide_kernel /
+// ras_conv_decide_kernel) and raises a per-subdomain stop word that every later launch honours,
+// so whatever was enqueued past the break point of source/schwarz_base.cpp:432-433 runs as
+// no-ops.  The host looks at a snapshot of the loop state once per chunk of iterations (the
+// snapshot taken at the end of chunk c is examined before chunk c + 2 is enqueued: the same
+// deterministic point on every process, so the NCCL call counts stay equal).
+//
+// Synchronous mode, per iteration and subdomain:
+//   unpack (waits for the neighbours' epoch) -> boundary update -> residual + norm ->
+//   [hub: gather the local norms, ncclAllGather across processes, ordered sum, decision] ->
+//   local solve -> restriction -> PUSH of the new boundary values for the next iteration.
+// The push sits at the tail of the iteration that produced the values (the reference sends at
+// the head of the next one and has a hook to overlap only its MPI_Wait,
+// source/restricted_schwarz.cpp:887-892, 965): the transfer and its flag latency run while the
+// neighbours are still in their own local solves, and the next iteration's unpack usually finds
+// the epoch already published.
 // =============================================================================
+struct Ras::Hub {
+    const Ctx *ctx = nullptr;
+    std::vector<Ras *> members;
+    int32_t P = 0;
+    const double **norm_ptrs = nullptr;
+    OuterState **state_ptrs = nullptr;
+    int32_t *slot = nullptr;
+    double *mine = nullptr, *all = nullptr, *history = nullptr;
+    size_t history_cap = 0;
+    OuterState *pinned = nullptr;            // 2 snapshots x nl
+    std::vector<cudaEvent_t> ev_chunk[2];
+    cudaEvent_t ev_decided = nullptr, ev_comm = nullptr;
+    ~Hub()
+    {
+        if (!ctx) return;
+        cudaSetDevice(ctx->device);
+        for (void *p : {(void *)norm_ptrs, (void *)state_ptrs, (void *)slot, (void *)mine,
+                        (void *)all, (void *)history})
+            if (p) cudaFree(p);
+        if (pinned) cudaFreeHost(pinned);
+        for (auto &v : ev_chunk)
+            for (cudaEvent_t e : v) cudaEventDestroy(e);
+        if (ev_decided) cudaEventDestroy(ev_decided);
+        if (ev_comm) cudaEventDestroy(ev_comm);
+    }
+};
+
+static Ras::Hub &ensure_hub(std::vector<Ras *> &subs, int32_t P)
+{
+    Ras *owner = subs[0];
+    if (owner->hub && owner->hub->members == subs && owner->hub->P == P) return *owner->hub;
+    owner->hub.reset(new Ras::Hub());
+    Ras::Hub &H = *owner->hub;
+    const Ctx &ctx = owner->ctx;
+    H.ctx = &ctx;
+    H.members = subs;
+    H.P = P;
+    const size_t nl = subs.size();
+    // the hub's kernels run on the first subdomain's device and touch the other subdomains'
+    // words: peers must see each other when the subdomains of a process span devices
+    for (Ras *r : subs)
+        if (r->ctx.device != ctx.device) {
+            int can = 0;
+            SCHWZ_CUDA(cudaDeviceCanAccessPeer(&can, ctx.device, r->ctx.device));
+            SCHWZ_REQUIRE(can, "subdomains of one process on devices without peer access");
+            ctx.use();
+            cudaError_t e = cudaDeviceEnablePeerAccess(r->ctx.device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) SCHWZ_CUDA(e);
+            cudaGetLastError();
+        }
+    // norms in rank order (the order the allgather / the ordered sum need)
+    std::vector<Ras *> by_rank(subs);
+    std::sort(by_rank.begin(), by_rank.end(), [](Ras *a, Ras *b) { return a->rank < b->rank; });
+    std::vector<const double *> np;
+    for (Ras *r : by_rank) np.push_back(r->resnorm_dev);
+    std::vector<OuterState *> sp;
+    std::vector<int32_t> sl;
+    for (Ras *r : subs) {
+        sp.push_back(r->state);
+        sl.push_back(r->rank);
+    }
+    H.norm_ptrs = ctx.upload(np.data(), nl);
+    H.state_ptrs = ctx.upload(sp.data(), nl);
+    H.slot = ctx.upload(sl.data(), nl);
+    H.mine = ctx.alloc_zero<double>(nl);
+    H.all = ctx.alloc_zero<double>((size_t)P);
+    SCHWZ_CUDA(cudaMallocHost((void **)&H.pinned, 2 * nl * sizeof(OuterState)));
+    for (auto &v : H.ev_chunk) {
+        v.resize(nl);
+        for (size_t i = 0; i < nl; ++i) {
+            subs[i]->ctx.use();
+            SCHWZ_CUDA(cudaEventCreateWithFlags(&v[i], cudaEventDisableTiming));
+        }
+    }
+    ctx.use();
+    SCHWZ_CUDA(cudaEventCreateWithFlags(&H.ev_decided, cudaEventDisableTiming));
+    SCHWZ_CUDA(cudaEventCreateWithFlags(&H.ev_comm, cudaEventDisableTiming));
+    ctx.sync();
+    return H;
+}
+
+// One synchronous exchange outside the loop: every subdomain's overlap / halo entries of x
+// become its neighbours' current values (what the final residual check needs after a run that
+// ended on its iteration budget, source/solve.cpp:1025-1085).  Collective over all processes.
+void ras_refresh_halo(std::vector<Ras *> &subs, int32_t P)
+{
+    if (P < 2) return;
+    std::vector<Ras *> by_rank(P, nullptr);
+    for (Ras *r : subs) by_rank[r->rank] = r;
+    for (Ras *r : subs) {
+        r->set_exchange_mode(EXCHANGE_PUT_GATHERED);
+        r->set_onesided(false);
+        r->exchange_push(0, r->tail_pending);
+        r->tail_pending = false;
+    }
+    for (Ras *r : subs) {
+        bool remote = false;
+        for (int32_t p : r->nbr_in) {
+            Ras *s = by_rank[p];
+            if (s) r->wait_push_of(*s);
+            else remote = true;
+        }
+        r->exchange_unpack(0, remote);
+    }
+    for (Ras *r : subs) r->ctx.sync();
+}
+
 void ras_run(std::vector<Ras *> &subs, const LoopOptions &o, LoopResult &res,
              double *history)
 {
@@ -630,164 +851,229 @@ void ras_run(std::vector<Ras *> &subs, const LoopOptions &o, LoopResult &res,
     SCHWZ_REQUIRE(nl > 0, "no subdomains");
     const bool multi_process = o.comm != nullptr && o.comm->nranks > 1;
     if (!multi_process) SCHWZ_REQUIRE(nl == P, "all subdomains must be local without a communicator");
-    std::vector<double> l_res(P, 0.0), mine(nl, 0.0);
     if (multi_process) {
-        Comm &c = *o.comm;
-        SCHWZ_REQUIRE(nl * c.nranks == P, "subdomains must be spread evenly over the processes");
-        if (c.cap < P) {
-            c.ctx->release(c.dev_in);
-            c.ctx->release(c.dev_out);
-            c.dev_in = c.ctx->alloc_zero<double>(nl);
-            c.dev_out = c.ctx->alloc_zero<double>(P);
-            c.cap = P;
-        }
+        SCHWZ_REQUIRE(nl * o.comm->nranks == P, "subdomains must be spread evenly over the processes");
+        for (int i = 0; i < nl; ++i)
+            SCHWZ_REQUIRE(subs[i]->rank == o.comm->rank * nl + i,
+                          "process p must hold the subdomains [p*nl, (p+1)*nl) in order");
     }
+    SCHWZ_REQUIRE(o.enable_onesided || o.exchange_mode == EXCHANGE_PUT_GATHERED,
+                  "Get / one-by-one exchanges exist in one-sided mode only");
     // map rank -> local subdomain (for same-process event waits)
     std::vector<Ras *> by_rank(P, nullptr);
     for (Ras *r : subs) by_rank[r->rank] = r;
-    SCHWZ_REQUIRE(o.enable_onesided || o.exchange_mode == EXCHANGE_PUT_GATHERED,
-                  "Get / one-by-one exchanges exist in one-sided mode only");
-    for (Ras *r : subs) r->set_exchange_mode(o.enable_onesided ? o.exchange_mode : EXCHANGE_PUT_GATHERED);
+    Ras::Hub &H = ensure_hub(subs, P);
+    if (multi_process && !o.enable_onesided && P != nl) {
+        // slot of local subdomain i inside the allgathered array = its rank; the local norms are
+        // contiguous in rank order by the requirement above
+        SCHWZ_REQUIRE(o.comm->ctx != nullptr, "communicator without a context");
+    }
+    for (Ras *r : subs) {
+        r->set_exchange_mode(o.enable_onesided ? o.exchange_mode : EXCHANGE_PUT_GATHERED);
+        r->set_onesided(o.enable_onesided != 0);
+        r->set_guarded(true);
+    }
+    struct Unguard {
+        std::vector<Ras *> &s;
+        ~Unguard()
+        {
+            for (Ras *r : s) r->set_guarded(false);
+        }
+    } unguard{subs};
+
+    // entry: a subdomain that converged in an earlier call stays finished until it is reset
+    std::vector<OuterState> st(nl);
+    int alive = 0;
+    for (int i = 0; i < nl; ++i) {
+        subs[i]->fetch_state(st[i]);
+        if (!st[i].stop) ++alive;
+    }
+    auto fill_result = [&](int iters_if_running) {
+        int fin = 0, last = -1;
+        for (int i = 0; i < nl; ++i) {
+            if (st[i].stop && st[i].error == OUTER_OK) {
+                ++fin;
+                last = std::max(last, st[i].finished_iter);
+            }
+        }
+        res.converged = fin == nl ? 1 : 0;
+        res.iters = fin == nl ? std::max(last, 0) : iters_if_running;
+        res.global_resnorm = st[0].gres;
+        res.global_resnorm0 = st[0].gres0;
+    };
+    if (alive == 0) {
+        fill_result(0);
+        res.iters = 0;
+        res.elapsed_s = 0.0;
+        return;
+    }
+    if (history) {
+        const size_t need = (size_t)o.max_iters * nl;
+        if (H.history_cap < need) {
+            H.ctx->release(H.history);
+            H.history = H.ctx->alloc<double>(need);
+            H.history_cap = need;
+        }
+        H.ctx->use();
+        SCHWZ_CUDA(cudaMemsetAsync(H.history, 0, need * sizeof(double), H.ctx->stream));
+    }
     for (Ras *r : subs) r->ctx.sync();
 
-    auto t0 = std::chrono::steady_clock::now();
-    int iter = 0, alive = nl;
-    bool all_done = false;
-    for (; iter < o.max_iters && !all_done; ++iter) {
-        // ---- 0 boundary exchange -------------------------------------------
-        if (P > 1 && !(o.enable_onesided && iter == 0)) {   // one-sided skips iter 0 (:725)
-            for (Ras *r : subs)
-                if (!r->finished) r->exchange_push(iter);
+    const cudaStream_t hub_stream = H.ctx->stream;
+    const double tol = o.tolerance;
+    const int32_t protocol = o.conv_tree ? 1 : (o.conv_accumulate ? 2 : 0);
+    auto enqueue_iteration = [&](int iter) {
+        const int32_t check =
+            (tol > 0.0 &&
+             (o.iter_offset ? ((iter > (o.max_iters * 0.05)) || o.max_iters < 1000) : true)) ? 1 : 0;
+        if (o.enable_onesided) {
+            // every subdomain runs its whole loop body on its own stream: no ordering between
+            // subdomains at all (one-sided semantics, source/restricted_schwarz.cpp:715-852)
+            for (int i = 0; i < nl; ++i) {
+                Ras *r = subs[i];
+                if (P > 1 && iter > 0) {   // one-sided skips iteration 0 (:725)
+                    r->exchange_push(iter);
+                    r->exchange_unpack(iter, false);
+                }
+                r->update_boundary();
+                r->local_residual();
+                r->conv_decide(protocol, tol, check, iter,
+                               history ? H.history + (size_t)iter * nl + i : nullptr);
+                r->local_solve();
+                r->restrict_to_x();
+            }
+            return;
+        }
+        // ---- 0 boundary exchange: the values were pushed at the tail of the previous pass ----
+        if (P > 1) {
             for (Ras *r : subs) {
-                if (r->finished) continue;
                 bool remote = false;
                 for (int32_t p : r->nbr_in) {
                     Ras *s = by_rank[p];
-                    if (s) {
-                        if (!o.enable_onesided && !s->finished) r->wait_push_of(*s);
-                    } else {
-                        remote = true;
-                    }
+                    if (s) r->wait_push_of(*s);
+                    else remote = true;
                 }
-                r->exchange_unpack(iter, remote && !o.enable_onesided);
+                r->exchange_unpack(iter, remote);
             }
         }
-        // ---- 1 boundary update, 2 convergence check ------------------------
+        // ---- 1 boundary update, 2 convergence check ----------------------------------------
         for (Ras *r : subs) {
-            if (r->finished) continue;
             r->update_boundary();
             r->local_residual();
-        }
-        for (int i = 0; i < nl; ++i) {
-            Ras *r = subs[i];
-            if (r->finished) continue;
-            r->ctx.use();
-            SCHWZ_CUDA(cudaMemcpyAsync(&mine[i], r->resnorm_dev, sizeof(double),
-                                       cudaMemcpyDeviceToHost, r->ctx.stream));
-        }
-        for (Ras *r : subs)
-            if (!r->finished) r->ctx.sync();
-        const double tol = o.tolerance;
-        for (int i = 0; i < nl; ++i) {
-            Ras *r = subs[i];
-            if (r->finished) continue;
-            r->resnorm = mine[i];
-            if (std::isnan(r->resnorm)) throw std::runtime_error("residual norm is NaN");
-            if (r->resnorm0 < 0.0) r->resnorm0 = r->resnorm;
-            if (history) history[(size_t)iter * nl + i] = r->resnorm;
-        }
-        const bool iter_cond =
-            o.iter_offset ? ((iter > (o.max_iters * 0.05)) || o.max_iters < 1000) : true;
-        if (!o.enable_onesided) {
-            // two-sided: allgather + ordered sum (source/solve.cpp:888-912)
-            if (multi_process) {
-                Comm &c = *o.comm;
-                c.ctx->use();
-                SCHWZ_CUDA(cudaMemcpyAsync(c.dev_in, mine.data(), nl * sizeof(double),
-                                           cudaMemcpyHostToDevice, c.ctx->stream));
-                comm_allgather_f64(c, c.dev_in, nl, c.dev_out);
-                SCHWZ_CUDA(cudaMemcpyAsync(l_res.data(), c.dev_out, P * sizeof(double),
-                                           cudaMemcpyDeviceToHost, c.ctx->stream));
-                c.ctx->sync();
-            } else {
-                for (int i = 0; i < nl; ++i) l_res[subs[i]->rank] = mine[i];
-            }
-            for (Ras *r : subs) {
-                int num_converged_p =
-                    (tol >= 0.0 && (r->resnorm * r->resnorm) / (r->resnorm0 * r->resnorm0) < tol * tol)
-                        ? 1 : 0;
-                if (tol > 0.0 && iter_cond) {
-                    int converged_all_local = 0;
-                    if (o.enable_global_check) {
-                        r->gres = 0.0;
-                        for (int j = 0; j < P; ++j) {
-                            if (l_res[j] != DBL_MAX) {
-                                r->gres += l_res[j];
-                            } else {
-                                r->gres = -1.0;
-                                break;
-                            }
-                        }
-                        if (r->gres >= 0.0) {
-                            if (r->gres0 < 0.0) r->gres0 = r->gres;
-                            if (r->gres / r->gres0 <= tol) converged_all_local++;
-                        }
-                        if (converged_all_local == 1) num_converged_p = P;
-                    } else {
-                        num_converged_p = 0;
-                    }
-                    r->num_converged = num_converged_p;
-                }
-                if (std::isnan(r->gres) || r->gres > 1e12)
-                    throw std::runtime_error("diverged");   // schwarz_base.cpp:424-428
-            }
-        } else {
-            // one-sided: local ratio test + flag protocol (source/solve.cpp:913-943)
-            std::vector<int32_t> counts(nl, 0);
-            for (int i = 0; i < nl; ++i) {
-                Ras *r = subs[i];
-                if (r->finished) continue;
-                if (!(tol > 0.0 && iter_cond)) continue;
-                const int cal = (r->resnorm / r->resnorm0 <= tol) ? 1 : 0;
-                if (o.conv_tree) r->conv_tree(cal);
-                else if (o.conv_accumulate) r->conv_accumulate(cal);
-                else r->conv_forward(cal);
+            if (r != subs[0]) {
                 r->ctx.use();
-                SCHWZ_CUDA(cudaMemcpyAsync(&counts[i], r->num_converged_dev, sizeof(int32_t),
-                                           cudaMemcpyDeviceToHost, r->ctx.stream));
-            }
-            for (int i = 0; i < nl; ++i) {
-                Ras *r = subs[i];
-                if (r->finished || !(tol > 0.0 && iter_cond)) continue;
-                r->ctx.sync();
-                r->num_converged = counts[i];
+                SCHWZ_CUDA(cudaEventRecord(r->ev_resid, r->ctx.stream));
             }
         }
-        // ---- break test (:432-433), 3 local solve, 4 restriction ------------
+        H.ctx->use();
+        for (Ras *r : subs)
+            if (r != subs[0]) SCHWZ_CUDA(cudaStreamWaitEvent(hub_stream, r->ev_resid, 0));
+        const double *all = H.mine;
+        launch_gather_norms(*H.ctx, nl, H.norm_ptrs, H.mine);
+        if (multi_process) {
+            // MPI_Allgather of the local norms (source/solve.cpp:890-891) as an on-stream
+            // ncclAllGather; the communicator's stream is ordered behind the hub's and back
+            Comm &c = *o.comm;
+            if (c.ctx->stream != hub_stream) {
+                SCHWZ_CUDA(cudaEventRecord(H.ev_comm, hub_stream));
+                c.ctx->use();
+                SCHWZ_CUDA(cudaStreamWaitEvent(c.ctx->stream, H.ev_comm, 0));
+            }
+            comm_allgather_f64(c, H.mine, nl, H.all);
+            if (c.ctx->stream != hub_stream) {
+                SCHWZ_CUDA(cudaEventRecord(H.ev_comm, c.ctx->stream));
+                H.ctx->use();
+                SCHWZ_CUDA(cudaStreamWaitEvent(hub_stream, H.ev_comm, 0));
+            }
+            all = H.all;
+        }
+        launch_ras_decide(*H.ctx, P, nl, all, H.slot, H.state_ptrs, tol, check,
+                          o.enable_global_check, iter, history ? H.history : nullptr);
+        SCHWZ_CUDA(cudaEventRecord(H.ev_decided, hub_stream));
+        for (Ras *r : subs)
+            if (r != subs[0]) {
+                r->ctx.use();
+                SCHWZ_CUDA(cudaStreamWaitEvent(r->ctx.stream, H.ev_decided, 0));
+            }
+        // ---- 3 local solve, 4 restriction, then the push for the next iteration -------------
         for (Ras *r : subs) {
-            if (r->finished) continue;
-            if (r->num_converged == P) {
-                r->finished = true;
-                r->finished_iter = iter;
-                --alive;
-            }
-        }
-        if (alive == 0) {
-            all_done = true;
-            break;
-        }
-        for (Ras *r : subs) {
-            if (r->finished) continue;
             r->local_solve();
             r->restrict_to_x();
+            if (P > 1) r->exchange_push(iter + 1);
+        }
+    };
+
+    auto t0 = std::chrono::steady_clock::now();
+    if (P > 1 && !o.enable_onesided)
+        for (Ras *r : subs) {
+            // the exchange of iteration 0: x as it stands now (a push left over from the
+            // previous call is rewritten with the same epoch)
+            r->exchange_push(0, r->tail_pending);
+            r->tail_pending = false;
+        }
+    // iterations enqueued between two looks at the loop state (SCHWZ_B200_OUTER_CHUNK)
+    const char *env_chunk_s = std::getenv("SCHWZ_B200_OUTER_CHUNK");
+    const int env_chunk = env_chunk_s ? std::atoi(env_chunk_s) : 0;
+    const int K = std::max(1, o.chunk > 0 ? o.chunk : (env_chunk > 0 ? env_chunk : 4));
+    int enq = 0, chunk_idx = 0;
+    bool done = false, failed = false;
+    auto examine = [&](int slot) {
+        int stopped = 0;
+        for (int i = 0; i < nl; ++i) {
+            subs[i]->ctx.use();
+            SCHWZ_CUDA(cudaEventSynchronize(H.ev_chunk[slot][i]));
+            const OuterState &S = H.pinned[(size_t)slot * nl + i];
+            if (S.error != OUTER_OK) failed = true;
+            if (S.stop) ++stopped;
+        }
+        if (stopped == nl || failed) done = true;
+    };
+    while (enq < o.max_iters && !done) {
+        const int end = std::min(o.max_iters, enq + K);
+        const int slot = chunk_idx & 1;
+        for (; enq < end; ++enq) {
+            enqueue_iteration(enq);
+            // the loop state of this iteration travels to the host behind it (no wait here)
+            for (int i = 0; i < nl; ++i) {
+                subs[i]->ctx.use();
+                SCHWZ_CUDA(cudaMemcpyAsync(&H.pinned[(size_t)slot * nl + i], subs[i]->state,
+                                           sizeof(OuterState), cudaMemcpyDeviceToHost,
+                                           subs[i]->ctx.stream));
+            }
+        }
+        for (int i = 0; i < nl; ++i) {
+            subs[i]->ctx.use();
+            SCHWZ_CUDA(cudaEventRecord(H.ev_chunk[slot][i], subs[i]->ctx.stream));
+        }
+        if (chunk_idx >= 1) examine(slot ^ 1);
+        ++chunk_idx;
+    }
+    if (P > 1 && !o.enable_onesided)
+        for (Ras *r : subs) r->tail_pending = true;
+    for (Ras *r : subs) r->ctx.sync();
+    H.ctx->sync();
+    if (multi_process) o.comm->ctx->sync();
+    auto t1 = std::chrono::steady_clock::now();
+    for (int i = 0; i < nl; ++i) subs[i]->fetch_state(st[i]);
+    if (history) {
+        H.ctx->use();
+        SCHWZ_CUDA(cudaMemcpyAsync(history, H.history, (size_t)o.max_iters * nl * sizeof(double),
+                                   cudaMemcpyDeviceToHost, H.ctx->stream));
+        H.ctx->sync();
+    }
+    for (int i = 0; i < nl; ++i) {
+        switch (st[i].error) {
+        case OUTER_HALO_TIMEOUT:
+            throw std::runtime_error("halo exchange timed out: subdomain " +
+                                     std::to_string(subs[i]->rank) +
+                                     " waited for a neighbour's boundary values longer than "
+                                     "SCHWZ_B200_HALO_TIMEOUT_MS");
+        case OUTER_NAN: throw std::runtime_error("residual norm is NaN");
+        case OUTER_DIVERGED: throw std::runtime_error("diverged");   // schwarz_base.cpp:424-428
+        default: break;
         }
     }
-    for (Ras *r : subs) r->ctx.sync();
-    auto t1 = std::chrono::steady_clock::now();
-    res.iters = iter;
-    res.converged = all_done ? 1 : 0;
-    res.global_resnorm = subs[0]->gres;
-    res.global_resnorm0 = subs[0]->gres0;
+    fill_result(enq);
     res.elapsed_s = std::chrono::duration<double>(t1 - t0).count();
 }
 

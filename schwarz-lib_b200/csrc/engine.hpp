@@ -31,7 +31,7 @@ void launch_cg_small(const Ctx &ctx, const DeviceCsr &A, const double *b, double
 bool gmres_small_fits(int64_t n, int m);
 void launch_gmres_small(const Ctx &ctx, const DeviceCsr &A, const double *b, double *x, double *V,
                         int32_t m, int32_t max_iters, double tol, double *resnorm_out,
-                        double *r0_out, int32_t *total_out);
+                        double *r0_out, int32_t *total_out, const int32_t *outer_stop = nullptr);
 
 // ---- local preconditioners (source/solve.cpp:486-652; precond.cu) --------------
 class TrsPlan;
@@ -89,7 +89,7 @@ public:
     void bench_step(int kind, double *scratch_x);   // 1: r update, 2: x/p update (timing only)
 
 private:
-    void iteration(double *x);
+    void iteration(double *x, cudaGraphConditionalHandle loop = 0);
     const Ctx &ctx_;
     const DeviceCsr &A_;
     int64_t n_;
@@ -110,6 +110,7 @@ private:
     };
     std::vector<Captured> graphs_;
     int plain_solves_ = 0;
+    bool not_graphable_ = false;   // a capture failed once: plain enqueue from then on
 };
 
 // ---- GMRES(m) (Ginkgo Gmres semantics; source/solve.cpp:486-567) -------------
@@ -119,7 +120,9 @@ public:
     ~GmresSolver();
     // right preconditioning: w = A M^-1 v_k ; x += M^-1 (V y)  (:496-556)
     void set_precond(Preconditioner *M);
-    void solve(const double *b, double *x, int32_t max_iters, double tol);
+    // outer_stop: optional device flag that turns the whole solve into a no-op
+    void solve(const double *b, double *x, int32_t max_iters, double tol,
+               const int32_t *outer_stop = nullptr);
     void result(int32_t *iters, double *resnorm, double *resnorm0);
 
 private:
@@ -242,15 +245,28 @@ public:
     void connect_conv(int32_t peer_rank, void *peer_base, const MailboxLayout &peer_layout);
     void set_exchange_mode(int32_t mode);
 
-    // stages of SchwarzBase::run's loop body (source/schwarz_base.cpp:387-452)
-    void exchange_push(int32_t iter);
-    void exchange_unpack(int32_t iter, bool wait_flags);
+    // stages of SchwarzBase::run's loop body (source/schwarz_base.cpp:387-452); every launch
+    // honours state->stop when `guarded` (the device-side outer loop), none does otherwise
+    // (stage-by-stage callers decide on the host).
+    // Exchange epochs (synchronous Put-gathered mode): every push carries the next epoch into the
+    // neighbours' receive buffer of that parity and publishes it; every unpack consumes the
+    // next epoch.  repush = write the LAST epoch again (same buffer, same flag value): what the
+    // outer loop does on entry when its previous call ended with a push nobody has unpacked.
+    // One-sided mode uses receive buffer 0 only and no flags: the receiver always sees the
+    // freshest values, as with the reference's single recv_buffer.
+    void exchange_push(int32_t iter, bool repush = false);
+    void exchange_unpack(int32_t iter, bool wait_flags, bool advance = true);
     void update_boundary();
     void local_residual();      // -> *resnorm_dev
     void local_solve();
     void restrict_to_x();
     void wait_push_of(const Ras &nbr);
     double true_residual_sq();
+    const double *solution_vector() const;   // what local_solve left: init_guess / local_sol
+    void set_guarded(bool g) { guarded_ = g; }
+    void set_onesided(bool o);
+    bool tail_pending = false;   // the last push of the previous ras_run has not been unpacked
+    void fetch_state(OuterState &out);       // synchronises
     // host-buffer entry points of the plugin path (what SolverRAS::initialize /
     // run move across PCIe: rhs in, solution out)
     void upload_rhs(const double *host_rhs_global);          // async H2D via pinned staging
@@ -271,6 +287,8 @@ public:
     double *x = nullptr, *local_rhs = nullptr, *local_sol = nullptr, *init_guess = nullptr,
            *work = nullptr;
     double *resnorm_dev = nullptr;
+    OuterState *state = nullptr;           // device-resident loop bookkeeping
+    cudaEvent_t ev_resid = nullptr;        // residual norm of this iteration is in resnorm_dev
     int32_t *num_converged_dev = nullptr, *conv_sent = nullptr;
     std::unique_ptr<DeviceCsr> A, I;
     std::unique_ptr<Preconditioner> precond;
@@ -282,10 +300,13 @@ public:
     int32_t last_push_iter = -1;
     int64_t local_nnz = 0;
 
-    // host-side convergence bookkeeping (source/solve.cpp:796-1005)
+    // host mirror of `state` (refreshed when ras_run polls / returns)
     double resnorm = -1.0, resnorm0 = -1.0, gres = 0.0, gres0 = -1.0;
     int32_t num_converged = 0, finished_iter = -1;
     bool finished = false;
+    void conv_decide(int32_t protocol, double tol, int32_t check, int32_t iter, double *history_slot);
+    struct Hub;                            // per-process decision hub (owned by the first subdomain)
+    std::unique_ptr<Hub> hub;
 
     int32_t *conv() const { return (int32_t *)(mailbox + mbox.conv_off); }
     int32_t *err_word() const { return (int32_t *)(mailbox + mbox.err_off); }
@@ -318,8 +339,11 @@ private:
     void **out_dst_dev_[2] = {nullptr, nullptr};
     unsigned long long **out_flag_dev_ = nullptr;
     int32_t **out_conv_dev_ = nullptr;
-    bool any_remote_ = false;
+    bool any_remote_ = false, guarded_ = false, onesided_ = false;
+    bool sol_in_guess_ = false;   // the last local solve left its result in init_guess (:781)
+    bool recv_dirty_ = false;   // reset_state ran: stale halo values may sit in the receive buffers
     int64_t push_epoch_ = 0, unpack_epoch_ = 0;
+    const int32_t *stop_ptr() const { return guarded_ ? &state->stop : nullptr; }
     std::vector<int32_t> l2g_local_;     // global ids of [own | overlap]
     double *pinned_rhs_ = nullptr;
     void upload_peer_tables();
@@ -328,6 +352,7 @@ private:
 
 struct LoopOptions {
     int32_t num_subdomains = 1, max_iters = 100;
+    int32_t chunk = 0;   // outer iterations enqueued between two host polls (0: default)
     double tolerance = 1e-6;
     int32_t enable_onesided = 0, enable_global_check = 0, conv_decentralized = 0, iter_offset = 0;
     // one-sided only: ExchangeMode, and 1 = centralised tree instead of flag flooding
@@ -340,5 +365,6 @@ struct LoopResult {
 };
 void ras_run(std::vector<Ras *> &subs, const LoopOptions &opt, LoopResult &res,
              double *resnorm_history);
+void ras_refresh_halo(std::vector<Ras *> &subs, int32_t P);
 
 }  // namespace schwz_b200

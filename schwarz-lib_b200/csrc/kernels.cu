@@ -8,6 +8,7 @@
 // >= 8 independent loads in flight per thread, x reused through L1/L2, fixed
 // summation order (bit-reproducible), no host round trips.
 #include <algorithm>
+#include <cfloat>
 
 #include "device.hpp"
 
@@ -23,6 +24,7 @@ int g_spmv_variant = 1;             // SCHWZ_B200_SPMV_VARIANT: launch shape of 
 Ctx::Ctx(int dev) : device(dev)
 {
     use();
+    SCHWZ_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
     SCHWZ_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     partials = alloc<double>(kMaxPartials);
     tickets = alloc_zero<unsigned int>(16);
@@ -442,14 +444,16 @@ static void launch_spmv_tma_cfg(const Ctx &ctx, const DeviceCsr &A, double alpha
                                 const int32_t *stop)
 {
     using Smem = SpmvSmem<RPT, STAGES>;
-    static bool configured[64] = {};
-    if (!configured[ctx.device]) {
+    // per-device, set once; several host threads (bench_ras rank threads) may arrive together:
+    // setting the attribute twice is harmless, the flag is an atomic
+    static std::atomic<bool> configured[64];
+    if (!configured[ctx.device].load(std::memory_order_acquire)) {
         SCHWZ_CUDA(cudaFuncSetAttribute(csr_spmv_tma_kernel<EPI, RPT, STAGES, CTAS>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)sizeof(Smem)));
-        configured[ctx.device] = true;
+        configured[ctx.device].store(true, std::memory_order_release);
     }
-    const int grid = std::min<int>(A.nblocks, kNumSMs * CTAS);
+    const int grid = std::min<int>(A.nblocks, ctx.num_sms * CTAS);
     csr_spmv_tma_kernel<EPI, RPT, STAGES, CTAS><<<grid, kSpmvThreads, sizeof(Smem), ctx.stream>>>(
         A.nblocks, A.blk_row, A.rp, A.ci, A.v, x, alpha, beta, y_in, y_out, dot_with, ctx.partials,
         ctx.tickets + 0, result, red_rows, stop);
@@ -540,17 +544,17 @@ __global__ void __launch_bounds__(kBlock)
     }
 }
 
-static int vec_grid(int64_t n)
+static int vec_grid(const Ctx &ctx, int64_t n)
 {
     int64_t need = (n + kBlock - 1) / kBlock;
-    return (int)std::max<int64_t>(1, std::min<int64_t>(need, kVecGrid));
+    return (int)std::max<int64_t>(1, std::min<int64_t>(need, ctx.vec_grid()));
 }
 
 void launch_dot(const Ctx &ctx, int64_t n, const double *a, const double *b, double *result,
                 bool sqrt_result)
 {
     ctx.use();
-    dot_kernel<<<vec_grid(n), kBlock, 0, ctx.stream>>>(n, a, b, ctx.partials, ctx.tickets + 1,
+    dot_kernel<<<vec_grid(ctx, n), kBlock, 0, ctx.stream>>>(n, a, b, ctx.partials, ctx.tickets + 1,
                                                        result, sqrt_result ? 1 : 0);
     SCHWZ_CUDA(cudaGetLastError());
     count_launch();
@@ -568,7 +572,7 @@ void launch_axpy(const Ctx &ctx, int64_t n, double alpha, const double *x, doubl
 {
     if (n <= 0) return;
     ctx.use();
-    axpy_kernel<<<vec_grid(n), kBlock, 0, ctx.stream>>>(n, alpha, x, y);
+    axpy_kernel<<<vec_grid(ctx, n), kBlock, 0, ctx.stream>>>(n, alpha, x, y);
     SCHWZ_CUDA(cudaGetLastError());
     count_launch();
 }
@@ -578,6 +582,44 @@ void launch_copy(const Ctx &ctx, int64_t n, const double *src, double *dst)
     if (n <= 0) return;
     ctx.use();
     SCHWZ_CUDA(cudaMemcpyAsync(dst, src, n * sizeof(double), cudaMemcpyDeviceToDevice, ctx.stream));
+}
+
+__global__ void __launch_bounds__(kBlock)
+    copy_guarded_kernel(int64_t n, const double *__restrict__ src, double *__restrict__ dst,
+                        const int32_t *stop)
+{
+    if (stop != nullptr && *stop != 0) return;
+    const bool vec = ((((uintptr_t)src) | ((uintptr_t)dst)) & 15) == 0;
+    if (vec) {
+        const int64_t n2 = n >> 1;
+        const double2 *s2 = reinterpret_cast<const double2 *>(src);
+        double2 *d2 = reinterpret_cast<double2 *>(dst);
+        const int64_t stride = (int64_t)gridDim.x * kBlock * 4;
+        for (int64_t i0 = (int64_t)blockIdx.x * kBlock * 4 + threadIdx.x; i0 < n2; i0 += stride) {
+            double2 v[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (i0 + (int64_t)j * kBlock < n2) v[j] = __ldcs(s2 + i0 + (int64_t)j * kBlock);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (i0 + (int64_t)j * kBlock < n2) d2[i0 + (int64_t)j * kBlock] = v[j];
+        }
+        if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) dst[n - 1] = src[n - 1];
+    } else {
+        for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n;
+             i += (int64_t)gridDim.x * kBlock)
+            dst[i] = src[i];
+    }
+}
+
+void launch_copy_guarded(const Ctx &ctx, int64_t n, const double *src, double *dst,
+                         const int32_t *stop)
+{
+    if (n <= 0) return;
+    ctx.use();
+    copy_guarded_kernel<<<vec_grid(ctx, (n + 7) / 8), kBlock, 0, ctx.stream>>>(n, src, dst, stop);
+    SCHWZ_CUDA(cudaGetLastError());
+    count_launch();
 }
 
 // =============================================================================
@@ -621,7 +663,7 @@ void launch_gather(const Ctx &ctx, int32_t n, const int32_t *idx, const double *
 {
     if (n <= 0) return;
     ctx.use();
-    gather_kernel<<<vec_grid(n), kBlock, 0, ctx.stream>>>(n, idx, from, into, op);
+    gather_kernel<<<vec_grid(ctx, n), kBlock, 0, ctx.stream>>>(n, idx, from, into, op);
     SCHWZ_CUDA(cudaGetLastError());
     count_launch();
 }
@@ -631,7 +673,7 @@ void launch_scatter(const Ctx &ctx, int32_t n, const int32_t *idx, const double 
 {
     if (n <= 0) return;
     ctx.use();
-    scatter_kernel<<<vec_grid(n), kBlock, 0, ctx.stream>>>(n, idx, from, into, op);
+    scatter_kernel<<<vec_grid(ctx, n), kBlock, 0, ctx.stream>>>(n, idx, from, into, op);
     SCHWZ_CUDA(cudaGetLastError());
     count_launch();
 }
@@ -640,8 +682,9 @@ void launch_scatter(const Ctx &ctx, int32_t n, const int32_t *idx, const double 
 // row_permute|inverse_permute out[perm[i]] = in[i]  (source/solve.cpp:717-720)
 __global__ void __launch_bounds__(kBlock)
     permute_kernel(int32_t n, const int32_t *__restrict__ perm, int inverse,
-                   const double *__restrict__ in, double *__restrict__ out)
+                   const double *__restrict__ in, double *__restrict__ out, const int32_t *stop)
 {
+    if (stop != nullptr && *stop != 0) return;
     for (int32_t i = blockIdx.x * kBlock + threadIdx.x; i < n; i += gridDim.x * kBlock) {
         if (inverse) out[perm[i]] = in[i];
         else out[i] = in[perm[i]];
@@ -649,11 +692,11 @@ __global__ void __launch_bounds__(kBlock)
 }
 
 void launch_permute(const Ctx &ctx, int32_t n, const int32_t *perm, int inverse,
-                    const double *in, double *out)
+                    const double *in, double *out, const int32_t *stop)
 {
     if (n <= 0) return;
     ctx.use();
-    permute_kernel<<<vec_grid(n), kBlock, 0, ctx.stream>>>(n, perm, inverse, in, out);
+    permute_kernel<<<vec_grid(ctx, n), kBlock, 0, ctx.stream>>>(n, perm, inverse, in, out, stop);
     SCHWZ_CUDA(cudaGetLastError());
     count_launch();
 }
@@ -669,8 +712,11 @@ void launch_permute(const Ctx &ctx, int32_t n, const int32_t *perm, int inverse,
 // iterations than are needed and never has to read a scalar back inside the
 // solve.
 // =============================================================================
+// `loop`: handle of the WHILE node around the iteration when the solve runs as a conditional
+// CUDA graph (0 otherwise): the kernels that take the stop decision also tell the graph
+// whether to go round again.
 __global__ void cg_init_kernel(CgScalars *s, int32_t max_iters, double tol,
-                               const int32_t *outer_stop)
+                               const int32_t *outer_stop, cudaGraphConditionalHandle loop)
 {
     // s->rho already holds ||b - A x0||^2 (fused into the residual SpMV)
     const double r0 = sqrt(s->rho);
@@ -687,13 +733,14 @@ __global__ void cg_init_kernel(CgScalars *s, int32_t max_iters, double tol,
     int stop = (0 >= max_iters) || (r0 < tol * r0);
     if (outer_stop != nullptr && *outer_stop != 0) stop = 1;
     s->stop = stop;
+    if (loop) cudaGraphSetConditional(loop, stop ? 0u : 1u);
 }
 
 void launch_cg_init(const Ctx &ctx, CgScalars *s, int32_t max_iters, double tol,
-                    const int32_t *outer_stop)
+                    const int32_t *outer_stop, cudaGraphConditionalHandle loop)
 {
     ctx.use();
-    cg_init_kernel<<<1, 1, 0, ctx.stream>>>(s, max_iters, tol, outer_stop);
+    cg_init_kernel<<<1, 1, 0, ctx.stream>>>(s, max_iters, tol, outer_stop, loop);
     SCHWZ_CUDA(cudaGetLastError());
     count_launch();
 }
@@ -765,7 +812,7 @@ void launch_cg_xp_update(const Ctx &ctx, int64_t n, const double *r, double *p, 
                          const CgScalars *s)
 {
     ctx.use();
-    cg_xp_update_kernel<<<vec_grid((n + 1) / 2), kBlock, 0, ctx.stream>>>(n, r, p, x, s);
+    cg_xp_update_kernel<<<vec_grid(ctx, (n + 1) / 2), kBlock, 0, ctx.stream>>>(n, r, p, x, s);
     SCHWZ_CUDA(cudaGetLastError());
     count_launch();
 }
@@ -773,7 +820,8 @@ void launch_cg_xp_update(const Ctx &ctx, int64_t n, const double *r, double *p, 
 // step_2b + next rho + stop test: r -= alpha q ; ||r||^2 ; alpha left pending for x
 __global__ void __launch_bounds__(kBlock)
     cg_r_update_kernel(int64_t n, double *__restrict__ r, const double *__restrict__ q,
-                       CgScalars *s, double *partials, unsigned int *ticket, int precond)
+                       CgScalars *s, double *partials, unsigned int *ticket, int precond,
+                       cudaGraphConditionalHandle loop)
 {
     __shared__ double s_warp[kBlock / 32];
     if (s->stop) return;
@@ -831,17 +879,19 @@ __global__ void __launch_bounds__(kBlock)
             s->iter = it;
             const double tau = sqrt(rho_new);
             s->resnorm = tau;
-            if (it >= s->max_iters || tau < s->tol * s->r0) s->stop = 1;
+            const bool stop = it >= s->max_iters || tau < s->tol * s->r0;
+            if (stop) s->stop = 1;
+            if (loop) cudaGraphSetConditional(loop, stop ? 0u : 1u);
         }
     }
 }
 
 void launch_cg_r_update(const Ctx &ctx, int64_t n, double *r, const double *q, CgScalars *s,
-                        bool precond)
+                        bool precond, cudaGraphConditionalHandle loop)
 {
     ctx.use();
-    cg_r_update_kernel<<<vec_grid((n + 1) / 2), kBlock, 0, ctx.stream>>>(
-        n, r, q, s, ctx.partials, ctx.tickets + 2, precond ? 1 : 0);
+    cg_r_update_kernel<<<vec_grid(ctx, (n + 1) / 2), kBlock, 0, ctx.stream>>>(
+        n, r, q, s, ctx.partials, ctx.tickets + 2, precond ? 1 : 0, loop);
     SCHWZ_CUDA(cudaGetLastError());
     count_launch();
 }
@@ -861,7 +911,7 @@ __global__ void __launch_bounds__(kBlock)
 void launch_cg_flush_x(const Ctx &ctx, int64_t n, double *x, const double *p, const CgScalars *s)
 {
     ctx.use();
-    cg_flush_x_kernel<<<vec_grid(n), kBlock, 0, ctx.stream>>>(n, x, p, s);
+    cg_flush_x_kernel<<<vec_grid(ctx, n), kBlock, 0, ctx.stream>>>(n, x, p, s);
     SCHWZ_CUDA(cudaGetLastError());
     count_launch();
 }
@@ -921,7 +971,7 @@ void launch_halo_pack_push(const Ctx &ctx, int32_t nseg, const int32_t *seg_off_
     if (nseg <= 0) return;
     SCHWZ_REQUIRE(nseg <= kMaxSeg, "too many out-neighbours for one push launch");
     ctx.use();
-    int grid = std::max(1, std::min((total + kBlock - 1) / kBlock, kVecGrid));
+    int grid = std::max(1, std::min((total + kBlock - 1) / kBlock, ctx.vec_grid()));
     if (f32)
         halo_pack_push_kernel<float><<<grid, kBlock, 0, ctx.stream>>>(nseg, seg_off_dev, total,
                                                                       src_idx, x, dst_ptrs, stop);
@@ -942,19 +992,26 @@ void launch_halo_pack_push(const Ctx &ctx, int32_t nseg, const int32_t *seg_off_
 // (synchronous semantics across processes); without, it scatters whatever the
 // buffer holds (asynchronous semantics).  The wait is bounded so a lost peer
 // cannot hang the GPU; on expiry error_flag is raised.
+long long g_halo_timeout_ns = 20ll * 1000 * 1000 * 1000;
+
 template <typename T>
 __global__ void __launch_bounds__(kBlock)
     halo_unpack_kernel(int32_t nseg, int32_t total, const int32_t *__restrict__ dst_idx,
                        const void *recv, double *__restrict__ x,
                        const unsigned long long *flags, unsigned long long epoch,
-                       int32_t *error_flag)
+                       int32_t *error_flag, long long timeout_ns, const int32_t *stop)
 {
+    if (stop != nullptr && *stop != 0) return;
     if (flags != nullptr) {
         if (threadIdx.x < nseg) {
-            long long spins = 0;
+            const unsigned long long t0 = global_timer_ns();
+            unsigned int spins = 0;
             while (ld_acquire_sys(flags + threadIdx.x) < epoch) {
                 __nanosleep(64);
-                if (++spins > (1ll << 24)) {   // ~1 s
+                if ((++spins & 1023u) == 0 &&
+                    (long long)(global_timer_ns() - t0) > timeout_ns) {
+                    // a lost peer must not hang the GPU: raise the error word (the host reads
+                    // it at its next poll and throws) and go on with what the buffer holds
                     if (error_flag) atomicExch(error_flag, 1);
                     break;
                 }
@@ -969,18 +1026,19 @@ __global__ void __launch_bounds__(kBlock)
 
 void launch_halo_unpack(const Ctx &ctx, int32_t nseg, int32_t total, const int32_t *dst_idx,
                         const void *recv, double *x, const unsigned long long *flags,
-                        unsigned long long epoch, int32_t *error_flag, bool f32)
+                        unsigned long long epoch, int32_t *error_flag, bool f32,
+                        const int32_t *stop)
 {
     if (nseg <= 0 || total <= 0) return;
     SCHWZ_REQUIRE(nseg <= kBlock, "too many in-neighbours for one unpack launch");
     ctx.use();
-    int grid = std::max(1, std::min((total + kBlock - 1) / kBlock, kVecGrid));
+    int grid = std::max(1, std::min((total + kBlock - 1) / kBlock, ctx.vec_grid()));
     if (f32)
-        halo_unpack_kernel<float><<<grid, kBlock, 0, ctx.stream>>>(nseg, total, dst_idx, recv, x,
-                                                                   flags, epoch, error_flag);
+        halo_unpack_kernel<float><<<grid, kBlock, 0, ctx.stream>>>(
+            nseg, total, dst_idx, recv, x, flags, epoch, error_flag, g_halo_timeout_ns, stop);
     else
-        halo_unpack_kernel<double><<<grid, kBlock, 0, ctx.stream>>>(nseg, total, dst_idx, recv, x,
-                                                                    flags, epoch, error_flag);
+        halo_unpack_kernel<double><<<grid, kBlock, 0, ctx.stream>>>(
+            nseg, total, dst_idx, recv, x, flags, epoch, error_flag, g_halo_timeout_ns, stop);
     SCHWZ_CUDA(cudaGetLastError());
     count_launch();
 }
@@ -1003,10 +1061,11 @@ __global__ void __launch_bounds__(kBlock)
     halo_put_elements_kernel(int32_t nseg, const int32_t *__restrict__ seg_off, int32_t total,
                              const int32_t *__restrict__ src_idx,
                              const int32_t *__restrict__ remote_slot, const double *__restrict__ x,
-                             double *const *__restrict__ peer_x)
+                             double *const *__restrict__ peer_x, const int32_t *stop)
 {
     __shared__ int32_t s_off[kMaxSeg + 1];
     __shared__ double *s_dst[kMaxSeg];
+    if (stop != nullptr && *stop != 0) return;
     if (threadIdx.x <= nseg) s_off[threadIdx.x] = seg_off[threadIdx.x];
     if (threadIdx.x < nseg) s_dst[threadIdx.x] = peer_x[threadIdx.x];
     __syncthreads();
@@ -1020,14 +1079,14 @@ __global__ void __launch_bounds__(kBlock)
 
 void launch_halo_put_elements(const Ctx &ctx, int32_t nseg, const int32_t *seg_off_dev,
                               int32_t total, const int32_t *src_idx, const int32_t *remote_slot,
-                              const double *x, double *const *peer_x)
+                              const double *x, double *const *peer_x, const int32_t *stop)
 {
     if (nseg <= 0 || total <= 0) return;
     SCHWZ_REQUIRE(nseg <= kMaxSeg, "too many out-neighbours for one put launch");
     ctx.use();
-    int grid = std::max(1, std::min((total + kBlock - 1) / kBlock, kVecGrid));
+    int grid = std::max(1, std::min((total + kBlock - 1) / kBlock, ctx.vec_grid()));
     halo_put_elements_kernel<<<grid, kBlock, 0, ctx.stream>>>(nseg, seg_off_dev, total, src_idx,
-                                                              remote_slot, x, peer_x);
+                                                              remote_slot, x, peer_x, stop);
     SCHWZ_CUDA(cudaGetLastError());
     count_launch();
 }
@@ -1037,10 +1096,12 @@ template <typename T>
 __global__ void __launch_bounds__(kBlock)
     halo_pull_kernel(int32_t nseg, const int32_t *__restrict__ seg_off, int32_t total,
                      const int32_t *__restrict__ dst_idx, const int32_t *__restrict__ src_idx,
-                     const void *const *__restrict__ src_ptrs, double *__restrict__ x)
+                     const void *const *__restrict__ src_ptrs, double *__restrict__ x,
+                     const int32_t *stop)
 {
     __shared__ int32_t s_off[kMaxSeg + 1];
     __shared__ const T *s_src[kMaxSeg];
+    if (stop != nullptr && *stop != 0) return;
     if (threadIdx.x <= nseg) s_off[threadIdx.x] = seg_off[threadIdx.x];
     if (threadIdx.x < nseg) s_src[threadIdx.x] = (const T *)src_ptrs[threadIdx.x];
     __syncthreads();
@@ -1054,18 +1115,18 @@ __global__ void __launch_bounds__(kBlock)
 
 void launch_halo_pull(const Ctx &ctx, int32_t nseg, const int32_t *seg_off_dev, int32_t total,
                       const int32_t *dst_idx, const int32_t *src_idx,
-                      const void *const *src_ptrs, double *x, bool f32)
+                      const void *const *src_ptrs, double *x, bool f32, const int32_t *stop)
 {
     if (nseg <= 0 || total <= 0) return;
     SCHWZ_REQUIRE(nseg <= kMaxSeg, "too many in-neighbours for one pull launch");
     ctx.use();
-    int grid = std::max(1, std::min((total + kBlock - 1) / kBlock, kVecGrid));
+    int grid = std::max(1, std::min((total + kBlock - 1) / kBlock, ctx.vec_grid()));
     if (f32)
         halo_pull_kernel<float><<<grid, kBlock, 0, ctx.stream>>>(nseg, seg_off_dev, total, dst_idx,
-                                                                 src_idx, src_ptrs, x);
+                                                                 src_idx, src_ptrs, x, stop);
     else
         halo_pull_kernel<double><<<grid, kBlock, 0, ctx.stream>>>(nseg, seg_off_dev, total, dst_idx,
-                                                                  src_idx, src_ptrs, x);
+                                                                  src_idx, src_ptrs, x, stop);
     SCHWZ_CUDA(cudaGetLastError());
     count_launch();
 }
@@ -1079,9 +1140,10 @@ void launch_halo_pull(const Ctx &ctx, int32_t nseg, const int32_t *seg_off_dev, 
 // conv lives in the peer-visible mailbox; remote MPI_Put ≙ relaxed system-scope
 // store, MPI_Win_flush ≙ __threadfence_system().
 // =============================================================================
-__global__ void conv_forward_kernel(int32_t P, int32_t me, int32_t converged_all_local,
-                                    int32_t *conv, int32_t *conv_sent, int32_t n_out,
-                                    int32_t *const *peer_conv, int32_t *num_converged)
+// body shared by the host-driven stage kernel and the device-side decision kernel below;
+// all threads of one CTA call it, the count is returned in every thread
+__device__ int conv_forward_body(int32_t P, int32_t me, int32_t converged_all_local, int32_t *conv,
+                                 int32_t *conv_sent, int32_t n_out, int32_t *const *peer_conv)
 {
     __shared__ int s_num;
     if (threadIdx.x == 0) {
@@ -1099,7 +1161,15 @@ __global__ void conv_forward_kernel(int32_t P, int32_t me, int32_t converged_all
     }
     __threadfence_system();
     __syncthreads();
-    if (threadIdx.x == 0) *num_converged = s_num;
+    return s_num;
+}
+
+__global__ void conv_forward_kernel(int32_t P, int32_t me, int32_t converged_all_local,
+                                    int32_t *conv, int32_t *conv_sent, int32_t n_out,
+                                    int32_t *const *peer_conv, int32_t *num_converged)
+{
+    const int num = conv_forward_body(P, me, converged_all_local, conv, conv_sent, n_out, peer_conv);
+    if (threadIdx.x == 0) *num_converged = num;
 }
 
 void launch_conv_forward(const Ctx &ctx, int32_t P, int32_t me, int32_t converged_all_local,
@@ -1120,10 +1190,10 @@ void launch_conv_forward(const Ctx &ctx, int32_t P, int32_t me, int32_t converge
 //   conv[2]          : "the root has seen everybody" (pushed down)
 // peer_conv[q] = conv array of subdomain q (null when q is not connected).
 // =============================================================================
-__global__ void conv_tree_kernel(int32_t P, int32_t me, int32_t converged_all_local, int32_t *conv,
-                                 int32_t *const *peer_conv, int32_t *num_converged)
+// thread 0 only; returns num_converged_procs
+__device__ int conv_tree_body(int32_t P, int32_t me, int32_t converged_all_local, int32_t *conv,
+                              int32_t *const *peer_conv)
 {
-    if (threadIdx.x != 0) return;
     const int c0 = ld_relaxed_sys_i32(conv + 0);
     const int c1 = ld_relaxed_sys_i32(conv + 1);
     if (((c0 == 1 && c1 == 1) || (c0 == 1 && me == P / 2 - 1) || (me >= P / 2 && c0 != 2)) &&
@@ -1143,10 +1213,16 @@ __global__ void conv_tree_kernel(int32_t P, int32_t me, int32_t converged_all_lo
             if (p < P) st_relaxed_sys_i32(peer_conv[p] + 2, 1);
         __threadfence_system();
         st_relaxed_sys_i32(conv + 1, ld_relaxed_sys_i32(conv + 1) + 1);
-        *num_converged = P;
-    } else {
-        *num_converged = 0;
+        return P;
     }
+    return 0;
+}
+
+__global__ void conv_tree_kernel(int32_t P, int32_t me, int32_t converged_all_local, int32_t *conv,
+                                 int32_t *const *peer_conv, int32_t *num_converged)
+{
+    if (threadIdx.x != 0) return;
+    *num_converged = conv_tree_body(P, me, converged_all_local, conv, peer_conv);
 }
 
 // Decentralised, accumulate variant (include/conv_tools.hpp:230-247,
@@ -1154,9 +1230,9 @@ __global__ void conv_tree_kernel(int32_t P, int32_t me, int32_t converged_all_lo
 // of EVERY other subdomain's flags (MPI_Accumulate SUM -> a system-scope atomic add over NVLink)
 // and to its own; num_converged_procs = its word 0.  The counter keeps growing as long as
 // subdomains stay converged - the reference's semantics, kept.
-__global__ void conv_accumulate_kernel(int32_t P, int32_t me, int32_t converged_all_local,
-                                       int32_t *conv, int32_t *const *peer_conv,
-                                       int32_t *num_converged)
+// all threads of one CTA; the count is valid in thread 0
+__device__ int conv_accumulate_body(int32_t P, int32_t me, int32_t converged_all_local,
+                                    int32_t *conv, int32_t *const *peer_conv)
 {
     const int t = threadIdx.x;
     if (converged_all_local > 0)
@@ -1164,7 +1240,15 @@ __global__ void conv_accumulate_kernel(int32_t P, int32_t me, int32_t converged_
             atomicAdd_system(j == me ? conv : peer_conv[j], 1);
     __threadfence_system();
     __syncthreads();
-    if (t == 0) *num_converged = ld_relaxed_sys_i32(conv + 0);
+    return ld_relaxed_sys_i32(conv + 0);
+}
+
+__global__ void conv_accumulate_kernel(int32_t P, int32_t me, int32_t converged_all_local,
+                                       int32_t *conv, int32_t *const *peer_conv,
+                                       int32_t *num_converged)
+{
+    const int num = conv_accumulate_body(P, me, converged_all_local, conv, peer_conv);
+    if (threadIdx.x == 0) *num_converged = num;
 }
 
 void launch_conv_accumulate(const Ctx &ctx, int32_t P, int32_t me, int32_t converged_all_local,
@@ -1183,6 +1267,149 @@ void launch_conv_tree(const Ctx &ctx, int32_t P, int32_t me, int32_t converged_a
     ctx.use();
     conv_tree_kernel<<<1, 32, 0, ctx.stream>>>(P, me, converged_all_local, conv, peer_conv,
                                                num_converged);
+    SCHWZ_CUDA(cudaGetLastError());
+    count_launch();
+}
+
+// =============================================================================
+// Device-side convergence decisions: what Solve::check_convergence does with host variables
+// (source/solve.cpp:796-1005) and the break test of SchwarzBase::run
+// (source/schwarz_base.cpp:424-433), on OuterState words the rest of the loop's launches honour.
+// =============================================================================
+__global__ void gather_norms_kernel(int32_t n, const double *const *__restrict__ norm_ptrs,
+                                    double *__restrict__ out)
+{
+    for (int i = threadIdx.x; i < n; i += blockDim.x) out[i] = *norm_ptrs[i];
+}
+
+void launch_gather_norms(const Ctx &ctx, int32_t n, const double *const *norm_ptrs, double *out)
+{
+    ctx.use();
+    gather_norms_kernel<<<1, 64, 0, ctx.stream>>>(n, norm_ptrs, out);
+    SCHWZ_CUDA(cudaGetLastError());
+    count_launch();
+}
+
+__device__ __forceinline__ bool outer_latch_norm(OuterState *S, double r, int32_t iter,
+                                                 double *history_slot)
+{
+    S->resnorm = r;
+    if (S->resnorm0 < 0.0) S->resnorm0 = r;
+    if (history_slot) *history_slot = r;
+    S->iter = iter + 1;
+    if (isnan(r)) {
+        S->error = OUTER_NAN;
+        S->stop = 1;
+        return false;
+    }
+    return true;
+}
+
+// Two-sided: allgather (done by the caller: `all`) + ordered sum + latch + ratio test
+// (source/solve.cpp:888-912), one thread per local subdomain.
+__global__ void ras_decide_kernel(int32_t P, int32_t nl, const double *__restrict__ all,
+                                  const int32_t *__restrict__ slot, OuterState *const *states,
+                                  double tol, int32_t check, int32_t enable_global_check,
+                                  int32_t iter, double *history)
+{
+    __shared__ double s_g;
+    if (threadIdx.x == 0) {
+        double g = 0.0;
+        for (int j = 0; j < P; ++j) {
+            if (all[j] != DBL_MAX) {
+                g += all[j];
+            } else {
+                g = -1.0;
+                break;
+            }
+        }
+        s_g = g;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < nl; i += blockDim.x) {
+        OuterState *S = states[i];
+        if (S->stop) continue;   // finished earlier (or failed): leave its record alone
+        if (!outer_latch_norm(S, all[slot[i]], iter, history ? history + (size_t)iter * nl + i : nullptr))
+            continue;
+        const double r = S->resnorm, r0 = S->resnorm0;
+        int num_converged_p = (tol >= 0.0 && (r * r) / (r0 * r0) < tol * tol) ? 1 : 0;
+        if (check) {
+            if (enable_global_check) {
+                S->gres = s_g;
+                if (s_g >= 0.0) {
+                    if (S->gres0 < 0.0) S->gres0 = s_g;
+                    if (s_g / S->gres0 <= tol) num_converged_p = P;
+                }
+            } else {
+                num_converged_p = 0;   // never raised outside the global check
+            }
+            S->num_converged = num_converged_p;
+        }
+        if (isnan(S->gres) || S->gres > 1e12) {   // schwarz_base.cpp:424-428
+            S->error = OUTER_DIVERGED;
+            S->stop = 1;
+            continue;
+        }
+        if (S->num_converged == P) {   // :432-433
+            S->finished_iter = iter;
+            S->stop = 1;
+        }
+    }
+}
+
+void launch_ras_decide(const Ctx &ctx, int32_t P, int32_t nl, const double *all,
+                       const int32_t *slot, OuterState *const *states, double tol,
+                       int32_t check, int32_t enable_global_check, int32_t iter, double *history)
+{
+    ctx.use();
+    ras_decide_kernel<<<1, 64, 0, ctx.stream>>>(P, nl, all, slot, states, tol, check,
+                                                enable_global_check, iter, history);
+    SCHWZ_CUDA(cudaGetLastError());
+    count_launch();
+}
+
+// One-sided: ratio test on the local norm, flag protocol, break test (source/solve.cpp:913-943)
+__global__ void ras_conv_decide_kernel(int32_t protocol, int32_t P, int32_t me, OuterState *S,
+                                       const double *resnorm_dev, double tol, int32_t check,
+                                       int32_t iter, double *history_slot, int32_t *conv,
+                                       int32_t *conv_sent, int32_t n_out,
+                                       int32_t *const *out_conv, int32_t *const *peer_conv,
+                                       int32_t *num_converged)
+{
+    __shared__ int s_go;
+    if (S->stop) return;
+    if (threadIdx.x == 0) s_go = outer_latch_norm(S, *resnorm_dev, iter, history_slot) ? 1 : 0;
+    __syncthreads();
+    if (!s_go || !check) return;
+    const int cal = (S->resnorm / S->resnorm0 <= tol) ? 1 : 0;
+    int num = 0;
+    if (protocol == 1) {
+        if (threadIdx.x == 0) num = conv_tree_body(P, me, cal, conv, peer_conv);
+    } else if (protocol == 2) {
+        num = conv_accumulate_body(P, me, cal, conv, peer_conv);
+    } else {
+        num = conv_forward_body(P, me, cal, conv, conv_sent, n_out, out_conv);
+    }
+    if (threadIdx.x == 0) {
+        *num_converged = num;
+        S->num_converged = num;
+        if (num == P) {
+            S->finished_iter = iter;
+            S->stop = 1;
+        }
+    }
+}
+
+void launch_ras_conv_decide(const Ctx &ctx, int32_t protocol, int32_t P, int32_t me,
+                            OuterState *state, const double *resnorm_dev, double tol,
+                            int32_t check, int32_t iter, double *history_slot, int32_t *conv,
+                            int32_t *conv_sent, int32_t n_out, int32_t *const *out_conv,
+                            int32_t *const *peer_conv, int32_t *num_converged)
+{
+    ctx.use();
+    ras_conv_decide_kernel<<<1, 128, 0, ctx.stream>>>(protocol, P, me, state, resnorm_dev, tol,
+                                                      check, iter, history_slot, conv, conv_sent,
+                                                      n_out, out_conv, peer_conv, num_converged);
     SCHWZ_CUDA(cudaGetLastError());
     count_launch();
 }

@@ -457,7 +457,7 @@ void Preconditioner::apply(const double *r, double *z, double *dot_result, const
     switch (kind_) {
     case PRECOND_BLOCK_JACOBI: {
         const int32_t ntiles = (n_ + kBlock - 1) / kBlock;
-        const int grid = std::min(ntiles, kVecGrid);
+        const int grid = std::min(ntiles, ctx_.vec_grid());
         block_jacobi_apply_kernel<<<grid, kBlock, 0, ctx_.stream>>>(
             n_, ntiles, dev_row_block_, dev_block_ptrs_, dev_block_off_, dev_blocks_, r, z,
             ctx_.partials, ctx_.tickets + 8, dot_result, stop);
@@ -473,7 +473,7 @@ void Preconditioner::apply(const double *r, double *z, double *dot_result, const
         Ltrs_->solve(in_, tmp_, stop);
         Utrs_->solve(tmp_, z, stop);
         if (dot_result) {
-            const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((n_ + kBlock - 1) / kBlock, kVecGrid));
+            const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((n_ + kBlock - 1) / kBlock, ctx_.vec_grid()));
             precond_dot_kernel<<<grid, kBlock, 0, ctx_.stream>>>(n_, r, z, ctx_.partials,
                                                                  ctx_.tickets + 8, dot_result, stop);
             SCHWZ_CUDA(cudaGetLastError());

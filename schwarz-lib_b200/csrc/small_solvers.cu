@@ -151,12 +151,12 @@ void launch_cg_small(const Ctx &ctx, const DeviceCsr &A, const double *b, double
 {
     ctx.use();
     const size_t smem = (4 * (size_t)A.nrows + kSmallBuf) * sizeof(double);
-    static bool configured[64] = {};
-    if (!configured[ctx.device]) {
+    static std::atomic<bool> configured[64];
+    if (!configured[ctx.device].load(std::memory_order_acquire)) {
         for (auto *k : {cg_small_kernel<128>, cg_small_kernel<256>, cg_small_kernel<1024>})
             SCHWZ_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             220 * 1024));
-        configured[ctx.device] = true;
+        configured[ctx.device].store(true, std::memory_order_release);
     }
     const int th = small_threads(A.nrows);
     auto *k = th == 128 ? cg_small_kernel<128> : th == 256 ? cg_small_kernel<256>
@@ -176,10 +176,12 @@ __global__ void __launch_bounds__(kSmallThreads, 1)
     gmres_small_kernel(int32_t n, const int32_t *__restrict__ rp_g, const int32_t *__restrict__ ci_g,
                        const double *__restrict__ v_g, const double *__restrict__ b, double *x,
                        double *V, int32_t m, int32_t max_iters, double tol, double *resnorm_out,
-                       double *r0_out, int32_t *total_out, int basis_in_smem, int matrix_in_smem)
+                       double *r0_out, int32_t *total_out, int basis_in_smem, int matrix_in_smem,
+                       const int32_t *outer_stop)
 {
     extern __shared__ __align__(16) double sm[];
     int phase = 0;
+    if (outer_stop != nullptr && *outer_stop != 0) return;
     const int32_t *rp = rp_g, *ci = ci_g;
     const double *v = v_g;
     double *w = sm;                               // n
@@ -333,15 +335,15 @@ bool gmres_small_fits(int64_t n, int m)
 
 void launch_gmres_small(const Ctx &ctx, const DeviceCsr &A, const double *b, double *x, double *V,
                         int32_t m, int32_t max_iters, double tol, double *resnorm_out,
-                        double *r0_out, int32_t *total_out)
+                        double *r0_out, int32_t *total_out, const int32_t *outer_stop)
 {
     ctx.use();
-    static bool configured[64] = {};
-    if (!configured[ctx.device]) {
+    static std::atomic<bool> configured[64];
+    if (!configured[ctx.device].load(std::memory_order_acquire)) {
         for (auto *k : {gmres_small_kernel<128>, gmres_small_kernel<256>, gmres_small_kernel<1024>})
             SCHWZ_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             220 * 1024));
-        configured[ctx.device] = true;
+        configured[ctx.device].store(true, std::memory_order_release);
     }
     const bool basis = gmres_small_smem(A.nrows, m, true) <= 220 * 1024;
     const bool matrix = gmres_small_smem(A.nrows, m, basis, A.nnz) <= 220 * 1024;
@@ -350,7 +352,7 @@ void launch_gmres_small(const Ctx &ctx, const DeviceCsr &A, const double *b, dou
                                                               : gmres_small_kernel<1024>;
     k<<<1, th, gmres_small_smem(A.nrows, m, basis, matrix ? A.nnz : -1), ctx.stream>>>(
         A.nrows, A.rp, A.ci, A.v, b, x, V, m, max_iters, tol, resnorm_out, r0_out, total_out,
-        basis ? 1 : 0, matrix ? 1 : 0);
+        basis ? 1 : 0, matrix ? 1 : 0, outer_stop);
     SCHWZ_CUDA(cudaGetLastError());
     count_launch();
 }

@@ -3,6 +3,7 @@
 // solve; stopping decisions are device flags that turn the remaining launches
 // into no-ops.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "engine.hpp"
@@ -58,7 +59,7 @@ int64_t CgSolver::bytes_per_iteration() const
            (M_ ? M_->bytes_per_apply() : 0);
 }
 
-void CgSolver::iteration(double *x)
+void CgSolver::iteration(double *x, cudaGraphConditionalHandle loop)
 {
     if (M_) {
         // z = M^-1 r with rho = r.z fused; the x/r update below then leaves rho alone and
@@ -71,7 +72,7 @@ void CgSolver::iteration(double *x)
     }
     launch_spmv(ctx_, A_, 1.0, p_, 0.0, nullptr, q_, EPI_DOT, p_, &s_->beta, (int32_t)n_,
                 &s_->stop);
-    launch_cg_r_update(ctx_, n_, r_, q_, s_, M_ != nullptr);
+    launch_cg_r_update(ctx_, n_, r_, q_, s_, M_ != nullptr, loop);
 }
 
 void CgSolver::solve(const double *b, double *x, int32_t max_iters, double tol,
@@ -91,39 +92,122 @@ void CgSolver::solve(const double *b, double *x, int32_t max_iters, double tol,
         for (int it = 0; it < max_iters; ++it) iteration(x);
         launch_cg_flush_x(ctx_, n_, x, p_, s_);
     };
-    if (max_iters <= kCgNoPoll) {
-        // The whole solve is a fixed launch sequence on fixed buffers (the stop decisions are
+    // Two graph shapes, both built at the second call with the same arguments:
+    //  * unrolled: initial residual, max_iters iterations, flush - a fixed launch sequence
+    //    whose kernels turn into no-ops once the stop flag is up.  Best when the budget is
+    //    what ends the solve (local_tol = 1e-12 with local_max_iters = 50);
+    //  * while:    the iteration is the body of a WHILE conditional node that the r update
+    //    (which takes the stop decision) re-arms from the device: the graph leaves the loop
+    //    after the last live iteration instead of running the rest of the budget as no-ops.
+    //    Best for inexact local solves (local_tol = 0.1 stops after a handful of iterations).
+    //    Also the only graph shape for budgets too long to unroll (local_max_iters = -1), which
+    //    otherwise need the host to poll the stop flag.
+    // SCHWZ_B200_CG_WHILE = 0 / 1 forces the choice; default: while when tol >= 1e-4 or the
+    // budget exceeds kCgNoPoll iterations.
+    const char *force_while_s = std::getenv("SCHWZ_B200_CG_WHILE");
+    const int force_while = force_while_s ? std::atoi(force_while_s) : -1;
+    const bool as_while =
+        force_while >= 0 ? force_while != 0 : (tol >= 1e-4 || max_iters > kCgNoPoll);
+    const bool graphable = g_use_cg_graph && !not_graphable_ && (!M_ || M_->kind() != PRECOND_ILU) &&
+                           (as_while || max_iters <= kCgNoPoll);
+    if (graphable) {
+        // The whole solve is a launch sequence on fixed buffers (the stop decisions are
         // device flags), so from the second call on it is replayed as ONE CUDA graph: at
         // mid-size subdomains (10^5..10^6 rows, kernels of a few microseconds) the 3*max_iters
         // launches are otherwise bound by launch latency.  Not with the ILU preconditioner,
         // whose triangular solves are graphs of their own.
-        const bool graphable = g_use_cg_graph && (!M_ || M_->kind() != PRECOND_ILU);
-        if (!graphable || ++plain_solves_ < 2) {
-            enqueue_all();
-            return;
-        }
-        for (const Captured &c : graphs_)
-            if (c.b == b && c.x == x && c.max_iters == max_iters && c.tol == tol &&
-                c.outer_stop == outer_stop) {
-                SCHWZ_CUDA(cudaGraphLaunch(c.exec, ctx_.stream));
-                count_launch(c.launches);
+        if (++plain_solves_ < 2) {
+            if (max_iters <= kCgNoPoll) {
+                enqueue_all();
                 return;
             }
-        if (graphs_.size() >= 2) {
-            cudaGraphExecDestroy(graphs_.front().exec);
-            graphs_.erase(graphs_.begin());
+        } else {
+            for (const Captured &c : graphs_)
+                if (c.b == b && c.x == x && c.max_iters == max_iters && c.tol == tol &&
+                    c.outer_stop == outer_stop) {
+                    SCHWZ_CUDA(cudaGraphLaunch(c.exec, ctx_.stream));
+                    count_launch(c.launches);
+                    return;
+                }
+            if (graphs_.size() >= 2) {
+                cudaGraphExecDestroy(graphs_.front().exec);
+                graphs_.erase(graphs_.begin());
+            }
+            ctx_.use();
+            const int64_t before = g_launches.load();
+            cudaGraph_t graph = nullptr;
+            bool capturing = false;
+            try {
+                if (as_while) {
+                    SCHWZ_CUDA(cudaGraphCreate(&graph, 0));
+                    cudaGraphConditionalHandle loop = 0;
+                    SCHWZ_CUDA(cudaGraphConditionalHandleCreate(&loop, graph, 0, 0));
+                    SCHWZ_CUDA(cudaStreamBeginCaptureToGraph(ctx_.stream, graph, nullptr, nullptr, 0,
+                                                             cudaStreamCaptureModeThreadLocal));
+                    capturing = true;
+                    launch_spmv(ctx_, A_, -1.0, x, 1.0, b, r_, EPI_NRM2SQ, nullptr, &s_->rho,
+                                (int32_t)n_, outer_stop);
+                    launch_cg_init(ctx_, s_, max_iters, tol, outer_stop, loop);
+                    cudaStreamCaptureStatus status;
+                    const cudaGraphNode_t *deps = nullptr;
+                    size_t ndeps = 0;
+                    cudaGraph_t cap = nullptr;
+                    SCHWZ_CUDA(cudaStreamGetCaptureInfo(ctx_.stream, &status, nullptr, &cap, &deps,
+                                                        &ndeps));
+                    cudaGraphNodeParams np = {};
+                    np.type = cudaGraphNodeTypeConditional;
+                    np.conditional.handle = loop;
+                    np.conditional.type = cudaGraphCondTypeWhile;
+                    np.conditional.size = 1;
+                    cudaGraphNode_t node;
+                    SCHWZ_CUDA(cudaGraphAddNode(&node, cap, deps, ndeps, &np));
+                    cudaGraph_t body = np.conditional.phGraph_out[0];
+                    SCHWZ_CUDA(cudaStreamUpdateCaptureDependencies(ctx_.stream, &node, 1,
+                                                                   cudaStreamSetCaptureDependencies));
+                    launch_cg_flush_x(ctx_, n_, x, p_, s_);
+                    SCHWZ_CUDA(cudaStreamEndCapture(ctx_.stream, &graph));
+                    capturing = false;
+                    SCHWZ_CUDA(cudaStreamBeginCaptureToGraph(ctx_.stream, body, nullptr, nullptr, 0,
+                                                             cudaStreamCaptureModeThreadLocal));
+                    capturing = true;
+                    iteration(x, loop);
+                    cudaGraph_t ignored = nullptr;
+                    SCHWZ_CUDA(cudaStreamEndCapture(ctx_.stream, &ignored));
+                    capturing = false;
+                } else {
+                    SCHWZ_CUDA(cudaStreamBeginCapture(ctx_.stream, cudaStreamCaptureModeThreadLocal));
+                    capturing = true;
+                    enqueue_all();
+                    SCHWZ_CUDA(cudaStreamEndCapture(ctx_.stream, &graph));
+                    capturing = false;
+                }
+                Captured c{b, x, max_iters, tol, outer_stop, nullptr,
+                           (int)(g_launches.load() - before)};
+                SCHWZ_CUDA(cudaGraphInstantiate(&c.exec, graph, 0));
+                cudaGraphDestroy(graph);
+                graph = nullptr;
+                graphs_.push_back(c);
+                SCHWZ_CUDA(cudaGraphLaunch(c.exec, ctx_.stream));
+                return;
+            } catch (...) {
+                // never leave the stream in capture mode: end the capture, drop the partial
+                // graph, remember not to try again, and solve without a graph below
+                if (capturing) {
+                    cudaGraph_t g2 = nullptr;
+                    cudaStreamEndCapture(ctx_.stream, &g2);
+                    if (g2 && g2 != graph) cudaGraphDestroy(g2);
+                }
+                if (graph) cudaGraphDestroy(graph);
+                cudaGetLastError();
+                not_graphable_ = true;
+                if (max_iters <= kCgNoPoll) {
+                    enqueue_all();
+                    return;
+                }
+            }
         }
-        ctx_.use();
-        const int64_t before = g_launches.load();
-        cudaGraph_t graph = nullptr;
-        SCHWZ_CUDA(cudaStreamBeginCapture(ctx_.stream, cudaStreamCaptureModeThreadLocal));
+    } else if (max_iters <= kCgNoPoll) {
         enqueue_all();
-        SCHWZ_CUDA(cudaStreamEndCapture(ctx_.stream, &graph));
-        Captured c{b, x, max_iters, tol, outer_stop, nullptr, (int)(g_launches.load() - before)};
-        SCHWZ_CUDA(cudaGraphInstantiate(&c.exec, graph, 0));
-        cudaGraphDestroy(graph);
-        graphs_.push_back(c);
-        SCHWZ_CUDA(cudaGraphLaunch(c.exec, ctx_.stream));
         return;
     }
     // r = b - A x, rho = r.r fused
@@ -204,7 +288,8 @@ __device__ __forceinline__ double *gm_y(double *base, int m) { return gm_g(base,
 
 // after r = b - A x with ||r|| in st->tmp: start a cycle
 __global__ void gmres_begin_cycle_kernel(GmresState *st, double *small, int first,
-                                         int32_t max_iters, double tol, int32_t m)
+                                         int32_t max_iters, double tol, int32_t m,
+                                         const int32_t *outer_stop)
 {
     if (!first && st->stop) return;
     const double rn = st->tmp;
@@ -215,6 +300,12 @@ __global__ void gmres_begin_cycle_kernel(GmresState *st, double *small, int firs
         st->max_iters = max_iters;
         st->m = m;
         st->stop = 0;
+        if (outer_stop != nullptr && *outer_stop != 0) {   // the whole solve is a no-op
+            st->stop = 1;
+            st->k = 0;
+            st->need_restart = 0;
+            return;
+        }
     }
     st->resnorm = rn;
     st->k = 0;
@@ -383,30 +474,32 @@ __global__ void __launch_bounds__(kBlock)
         x[i] += pv[i];
 }
 
-static int vgrid(int64_t n)
+static int vgrid(const Ctx &ctx, int64_t n)
 {
-    return (int)std::max<int64_t>(1, std::min<int64_t>((n + kBlock - 1) / kBlock, kVecGrid));
+    return (int)std::max<int64_t>(1, std::min<int64_t>((n + kBlock - 1) / kBlock, ctx.vec_grid()));
 }
 
-void GmresSolver::solve(const double *b, double *x, int32_t max_iters, double tol)
+void GmresSolver::solve(const double *b, double *x, int32_t max_iters, double tol,
+                        const int32_t *outer_stop)
 {
     ctx_.use();
     cudaStream_t st = ctx_.stream;
     const size_t small = (size_t)(m_ + 1) * m_ + 4 * (size_t)m_ + 8;
     GmresState *S = (GmresState *)(small_ + small);
     double *H = small_;
-    const int g = vgrid(n_);
+    const int g = vgrid(ctx_, n_);
     if (g_use_small_solvers && gmres_small_fits(n_, m_) && !M_) {
-        launch_gmres_small(ctx_, A_, b, x, V_, m_, max_iters, tol, &S->resnorm, &S->r0, &S->total);
+        launch_gmres_small(ctx_, A_, b, x, V_, m_, max_iters, tol, &S->resnorm, &S->r0, &S->total,
+                           outer_stop);
         return;
     }
 
     auto begin_cycle = [&](int first) {
         // w = b - A x ; tmp = ||w|| ; V0 = w / ||w||
         launch_spmv(ctx_, A_, -1.0, x, 1.0, b, w_, EPI_NRM2, nullptr, &S->tmp, (int32_t)n_,
-                    nullptr);
-        gmres_begin_cycle_kernel<<<1, 1, 0, st>>>(S, small_, first, max_iters, tol, m_);
-        gmres_scale_kernel<<<g, kBlock, 0, st>>>(n_, w_, V_, &S->tmp, S, 0);
+                    outer_stop);
+        gmres_begin_cycle_kernel<<<1, 1, 0, st>>>(S, small_, first, max_iters, tol, m_, outer_stop);
+        gmres_scale_kernel<<<g, kBlock, 0, st>>>(n_, w_, V_, &S->tmp, S, 1);
         count_launch(2);
     };
     // x += V y, or x += M^-1 (V y) with a preconditioner (V y accumulated from zero, columns
@@ -440,7 +533,7 @@ void GmresSolver::solve(const double *b, double *x, int32_t max_iters, double to
             // the cycle restart must not run once stopped: guard through S->stop
             launch_spmv(ctx_, A_, -1.0, x, 1.0, b, w_, EPI_NRM2, nullptr, &S->tmp, (int32_t)n_,
                         &S->stop);
-            gmres_begin_cycle_kernel<<<1, 1, 0, st>>>(S, small_, 0, max_iters, tol, m_);
+            gmres_begin_cycle_kernel<<<1, 1, 0, st>>>(S, small_, 0, max_iters, tol, m_, nullptr);
             gmres_scale_kernel<<<g, kBlock, 0, st>>>(n_, w_, V_, &S->tmp, S, 1);
             count_launch(2);
             k = 0;
@@ -838,12 +931,12 @@ void TrsPlan::solve(const double *b, double *x, const int32_t *stop)
             const int32_t l = sg.a;
             const int32_t rows = level_ptr_[l + 1] - level_ptr_[l];
             if (sg.mode == 1) {
-                const int grid = std::min((rows + kBlock - 1) / kBlock, kVecGrid);
+                const int grid = std::min((rows + kBlock - 1) / kBlock, ctx_.vec_grid());
                 trs_level_thread_kernel<<<grid, kBlock, 0, ctx_.stream>>>(
                     level_ptr_[l], level_ptr_[l + 1], order_, rp_, ci_, v_, inv_diag_, b, x, stop);
                 continue;
             }
-            const int grid = std::min((rows + kTrsWarps - 1) / kTrsWarps, kVecGrid);
+            const int grid = std::min((rows + kTrsWarps - 1) / kTrsWarps, ctx_.vec_grid());
             trs_levels_kernel<<<grid, kBlock, 0, ctx_.stream>>>(level_ptr_[l], level_ptr_[l + 1],
                                                                 order_, rp_, ci_, v_, inv_diag_,
                                                                 b, x, stop);

@@ -1016,6 +1016,7 @@ void SolverRAS<V, I, M>::exchange_boundary(const Settings &settings, const Metad
         const auto &c = settings.comm_settings;
         const int32_t mode = (c.enable_put ? 0 : 1) + (c.enable_one_by_one ? 2 : 0);
         B200_CHECK(schwz_b200_ras_set_exchange_mode(ras, mode));
+        B200_CHECK(schwz_b200_ras_set_onesided(ras, 1));
         B200_CHECK(schwz_b200_ras_exchange_push(ras, metadata.iter_count));
         B200_CHECK(schwz_b200_ras_exchange_unpack(ras, metadata.iter_count, 0));
         return;

@@ -705,6 +705,9 @@ class Ras:
         return int(n.value)
 
     # loop stages
+    def set_onesided(self, on):
+        _chk(load().schwz_b200_ras_set_onesided(self.h, C.c_int32(int(on))))
+
     def exchange_push(self, it):
         _chk(load().schwz_b200_ras_exchange_push(self.h, C.c_int32(it)))
 
@@ -824,6 +827,13 @@ def remote_connection_plan(setup, my_ranks, nbr_in_of):
 def connect_local(subs, setup):
     arr = (C.c_void_p * len(subs))(*[s.h for s in subs])
     _chk(load().schwz_b200_ras_connect_local(arr, C.c_int32(len(subs)), setup.h))
+
+
+def refresh_halo(subs, num_subdomains):
+    """one synchronous halo exchange outside the loop (collective): x's overlap / halo entries
+    become the neighbours' current values"""
+    arr = (C.c_void_p * len(subs))(*[s.h for s in subs])
+    _chk(load().schwz_b200_ras_refresh_halo(arr, C.c_int32(len(subs)), C.c_int32(num_subdomains)))
 
 
 def ras_run(subs, num_subdomains, max_iters, tolerance=1e-6, enable_onesided=False,

@@ -289,12 +289,7 @@ def test_full_size_cfg2_properties(sz):
         assert h[0, r] == np.sqrt(float(subs[r].local_size_x))
     assert np.all(h[1] > 0) and np.all(np.isfinite(h))
     # halo consistency after one more exchange
-    for s in subs:
-        s.exchange_push(0)
-    for s in subs:
-        s.sync()
-    for s in subs:
-        s.exchange_unpack(0)
+    sz.refresh_halo(subs, P)
     fr = setup.first_row()
     xs = [s.x() for s in subs]
     for r in (0, 3, 7):
@@ -307,8 +302,15 @@ def test_full_size_cfg2_properties(sz):
             m = owner == q
             want[m] = xs[q][ext[m] - fr[q]]
         assert np.array_equal(xs[r][ls:], want)
-    # determinism: same state, same three iterations -> identical norms
-    state = [x.copy() for x in xs]
+    # determinism: zero state again, same three iterations -> identical norms and iterates
+    for s in subs:
+        s.reset()
+    out2 = sz.ras_run(subs, P, 3, tolerance=1e-6, enable_global_check=True, history=True)
+    assert np.array_equal(out2["history"], h)
+    assert out2["global_resnorm"] == out["global_resnorm"]
+    sz.refresh_halo(subs, P)
+    for r in (0, 3, 7):
+        assert np.array_equal(subs[r].x(), xs[r])
     for s in subs:
         s.close()
     for c in ctxs:
