@@ -102,12 +102,14 @@ void CgSolver::solve(const double *b, double *x, int32_t max_iters, double tol,
     //    Best for inexact local solves (local_tol = 0.1 stops after a handful of iterations).
     //    Also the only graph shape for budgets too long to unroll (local_max_iters = -1), which
     //    otherwise need the host to poll the stop flag.
-    // SCHWZ_B200_CG_WHILE = 0 / 1 forces the choice; default: while when tol >= 1e-4 or the
-    // budget exceeds kCgNoPoll iterations.
+    // Measured on cfg2 (8 strips of 8.4 M rows on one B200): 83.8 ms per outer iteration as a
+    // WHILE graph against 83.4 - 84.5 ms unrolled at 50 iterations, 108.8 against 108.4 ms at 70
+    // (profiles/r2_while_graph.md) - the loop node costs nothing measurable, so it is the
+    // default; SCHWZ_B200_CG_WHILE=0 selects the unrolled graph (budgets up to kCgNoPoll).
     const char *force_while_s = std::getenv("SCHWZ_B200_CG_WHILE");
     const int force_while = force_while_s ? std::atoi(force_while_s) : -1;
     const bool as_while =
-        force_while >= 0 ? force_while != 0 : (tol >= 1e-4 || max_iters > kCgNoPoll);
+        force_while >= 0 ? (force_while != 0 || max_iters > kCgNoPoll) : true;
     const bool graphable = g_use_cg_graph && !not_graphable_ && (!M_ || M_->kind() != PRECOND_ILU) &&
                            (as_while || max_iters <= kCgNoPoll);
     if (graphable) {

@@ -43,6 +43,62 @@ CASES = {
 }
 
 
+# Sampled goldens: the same reference runs at sizes whose full vectors would not be "small
+# fixtures".  Stored per rank: sizes, neighbour lists, the local residual norm of every outer
+# iteration, and for the iterations in `snap` the norm of the iterate over l2g plus its values at
+# a fixed set of positions of l2g (every OWN_STRIDE-th own entry, every EXT_STRIDE-th overlap /
+# halo entry - the part the exchange writes).
+OWN_STRIDE, EXT_STRIDE = 251, 7
+SAMPLED_CASES = {
+    # the bench workload (BASELINE.json configs[1]: strips, CG with local_max_iters = 50,
+    # synchronous exchange, global check) at 1024^2: first 13 outer iterations
+    "cfg2_lap1024_P8_cg50": dict(P=8, laplacian_n=1024, partition="regular", max_iters=13,
+                                 tolerance=1e-30, local_max_iters=50, snap=[1, 2, 4, 8, 12]),
+}
+
+
+def sample_positions(local_size, n_known):
+    own = np.arange(0, local_size, OWN_STRIDE)
+    ext = np.arange(local_size, n_known, EXT_STRIDE)
+    return np.concatenate([own, ext]).astype(np.int64)
+
+
+def main_sampled():
+    import ref as R
+    for name, c in SAMPLED_CASES.items():
+        c = dict(c)
+        P = c.pop("P")
+        snap = c.pop("snap")
+        rr = R.Run(P, overlap=2, local_tol=1e-12, enable_global_check=True, record_iterates=True, **c)
+        out = {"first_row": rr.vec("first_row", 0), "snap": np.array(snap, np.int32),
+               "iters": np.array([rr.iter_count(r) for r in range(P)], np.int32),
+               "strides": np.array([OWN_STRIDE, EXT_STRIDE], np.int32)}
+        for r in range(P):
+            s = rr.sizes(r)
+            out["sizes_%d" % r] = np.array([s[k] for k in ("local_size", "local_size_x", "overlap_size",
+                                                          "nnz_local", "nnz_interface")], np.int64)
+            g2l = rr.vec("g2l", r)
+            n_known = int(g2l.max())
+            l2g = rr.vec("l2g", r)[:n_known]
+            pos = sample_positions(s["local_size"], n_known)
+            out["n_known_%d" % r] = np.array([n_known], np.int64)
+            out["l2g_sample_%d" % r] = l2g[pos]
+            out["l2g_checksum_%d" % r] = np.array([int(l2g.astype(np.int64).sum()),
+                                                    int((l2g.astype(np.int64) * (np.arange(n_known) % 1009)).sum())],
+                                                   np.int64)
+            out["nbr_in_%d" % r] = rr.vec("neighbors_in", r)
+            out["nbr_out_%d" % r] = rr.vec("neighbors_out", r)
+            out["local_res_%d" % r] = rr.vec("local_residuals", r)
+            for k in snap:
+                if k < rr.num_iterates(r):
+                    x = rr.iterate(r, k)[l2g]
+                    out["xnorm_%d_%d" % (r, k)] = np.array([np.linalg.norm(x)])
+                    out["x_%d_%d" % (r, k)] = x[pos]
+        path = os.path.join(HERE, "refs_%s.npz" % name)
+        np.savez_compressed(path, **out)
+        print(name, "iters", out["iters"].tolist(), os.path.getsize(path), "bytes")
+
+
 def main():
     import ref as R
     for name, c in CASES.items():
@@ -83,4 +139,8 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "sampled":
+        main_sampled()
+    else:
+        main()
+        main_sampled()
