@@ -162,6 +162,9 @@ int schwz_b200_trs_analyze(schwz_ctx *ctx, int32_t n, const int32_t *host_rowptr
 int schwz_b200_trs_destroy(schwz_trs *t);
 int schwz_b200_trs_solve(schwz_trs *t, const double *dev_b, double *dev_x);
 int schwz_b200_trs_levels(const schwz_trs *t, int32_t *num_levels);
+/* synchronises; non-zero: a dependency wait of the one-kernel solve ran into its time bound
+ * (the solve is then void).  SCHWZ_B200_TRS_LEVELS=1 selects the level-per-launch graph. */
+int schwz_b200_trs_error(schwz_trs *t, int32_t *err);
 /* out[i] = in[perm[i]] (inverse == 0) or out[perm[i]] = in[i] (inverse != 0) */
 int schwz_b200_permute(schwz_ctx *ctx, int32_t n, const int32_t *dev_perm,
                        int inverse, const double *dev_in, double *dev_out);

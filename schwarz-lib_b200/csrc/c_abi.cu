@@ -412,6 +412,12 @@ int schwz_b200_trs_solve(schwz_trs *t, const double *b, double *x)
     t->impl->solve(b, x);
     ABI_END
 }
+int schwz_b200_trs_error(schwz_trs *t, int32_t *err)
+{
+    ABI_BEGIN
+    *err = t->impl->error();
+    ABI_END
+}
 int schwz_b200_trs_levels(const schwz_trs *t, int32_t *num_levels)
 {
     ABI_BEGIN

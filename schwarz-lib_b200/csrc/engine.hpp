@@ -183,6 +183,23 @@ private:
         cudaGraphExec_t exec;
     };
     std::vector<Captured> graphs_;
+    // dependency-driven solve (one persistent kernel): work items in dependency order,
+    // claimed dynamically; a value that is still the "unset" bit pattern is not ready yet
+    struct Item {
+        int32_t kind, a, b, c;
+    };
+    Item *items_ = nullptr;
+    int32_t num_items_ = 0, num_chain_rows_ = 0;
+    int32_t *counter_ = nullptr;        // [0] next item, [1] error / abort word
+    double *t_ = nullptr;               // block right-hand sides, one slot per chain row
+    int32_t *blk_pos0_ = nullptr, *blk_nb_ = nullptr, *blk_ord0_ = nullptr;
+    int64_t *blk_dinv_off_ = nullptr;
+    void solve_levels(const double *b, double *x, const int32_t *stop);
+    void solve_flow(const double *b, double *x, const int32_t *stop);
+
+public:
+    int32_t num_items() const { return num_items_; }
+    int32_t error();                    // synchronises; non-zero: a wait timed out
 };
 
 struct RasOptions {

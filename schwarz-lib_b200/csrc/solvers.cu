@@ -110,7 +110,11 @@ void CgSolver::solve(const double *b, double *x, int32_t max_iters, double tol,
     const int force_while = force_while_s ? std::atoi(force_while_s) : -1;
     const bool as_while =
         force_while >= 0 ? (force_while != 0 || max_iters > kCgNoPoll) : true;
-    const bool graphable = g_use_cg_graph && !not_graphable_ && (!M_ || M_->kind() != PRECOND_ILU) &&
+    // (the level-per-launch triangular solves of the ILU preconditioner are graphs of their
+    // own and cannot be captured; the one-kernel solves can)
+    const char *trs_levels = std::getenv("SCHWZ_B200_TRS_LEVELS");
+    const bool ilu_levels = M_ && M_->kind() == PRECOND_ILU && trs_levels && trs_levels[0] == '1';
+    const bool graphable = g_use_cg_graph && !not_graphable_ && !ilu_levels &&
                            (as_while || max_iters <= kCgNoPoll);
     if (graphable) {
         // The whole solve is a launch sequence on fixed buffers (the stop decisions are
@@ -893,6 +897,45 @@ TrsPlan::TrsPlan(const Ctx &ctx, int32_t n, const int32_t *rp, const int32_t *ci
         dinv_ = ctx.upload(dinv.data(), dinv.size());
         block_t_ = ctx.alloc_zero<double>(kTrsBlock);
     }
+
+    // ---- work items of the dependency-driven solve, in an order in which every item only
+    // waits for items before it: the wide levels in level order (a chunk of <= 32 short rows
+    // for the lanes of a warp, or one row per warp), then per block its right-hand-side rows
+    // followed by the rows of the explicit inverse ------------------------------------------
+    std::vector<Item> items;
+    std::vector<int32_t> bpos0, bnb, bord0;
+    std::vector<int64_t> boff;
+    int32_t ord = 0;
+    for (const Segment &sg : segments_) {
+        if (sg.kind == 0) {
+            const int32_t p0 = level_ptr_[sg.a], p1 = level_ptr_[sg.a + 1];
+            int64_t lnnz = 0;
+            for (int32_t i = p0; i < p1; ++i) lnnz += rp[order[i] + 1] - rp[order[i]] - 1;
+            if (lnnz <= 8 * (int64_t)(p1 - p0)) {
+                for (int32_t q = p0; q < p1; q += 32) items.push_back({0, q, std::min(32, p1 - q), 0});
+            } else {
+                for (int32_t q = p0; q < p1; ++q) items.push_back({1, q, 0, 0});
+            }
+        } else {
+            const int32_t blk = (int32_t)bpos0.size();
+            bpos0.push_back(sg.a);
+            bnb.push_back(sg.b);
+            bord0.push_back(ord);
+            boff.push_back(sg.dinv_off);
+            for (int32_t i = 0; i < sg.b; ++i) items.push_back({2, sg.a + i, ord + i, 0});
+            for (int32_t i = 0; i < sg.b; ++i) items.push_back({3, blk, i, 0});
+            ord += sg.b;
+        }
+    }
+    num_items_ = (int32_t)items.size();
+    num_chain_rows_ = ord;
+    items_ = ctx.upload(items.data(), items.size());
+    counter_ = ctx.alloc_zero<int32_t>(4);
+    t_ = ctx.alloc_zero<double>(std::max(ord, 1));
+    blk_pos0_ = ctx.upload(bpos0.data(), bpos0.size());
+    blk_nb_ = ctx.upload(bnb.data(), bnb.size());
+    blk_ord0_ = ctx.upload(bord0.data(), bord0.size());
+    blk_dinv_off_ = ctx.upload(boff.data(), boff.size());
 }
 
 TrsPlan::~TrsPlan()
@@ -908,9 +951,16 @@ TrsPlan::~TrsPlan()
     ctx_.release(chain_v_);
     ctx_.release(dinv_);
     ctx_.release(block_t_);
+    ctx_.release(items_);
+    ctx_.release(counter_);
+    ctx_.release(t_);
+    ctx_.release(blk_pos0_);
+    ctx_.release(blk_nb_);
+    ctx_.release(blk_ord0_);
+    ctx_.release(blk_dinv_off_);
 }
 
-void TrsPlan::solve(const double *b, double *x, const int32_t *stop)
+void TrsPlan::solve_levels(const double *b, double *x, const int32_t *stop)
 {
     ctx_.use();
     if (n_ == 0) return;
@@ -959,6 +1009,233 @@ void TrsPlan::solve(const double *b, double *x, const int32_t *stop)
     graphs_.push_back(c);
     SCHWZ_CUDA(cudaGraphLaunch(c.exec, ctx_.stream));
     count_launch(num_launches());
+}
+
+// =============================================================================
+// Dependency-driven solve: ONE persistent kernel per triangular solve instead of one launch
+// per level (331 dependent launches for the cfg5 factor).  The work items above are claimed in
+// order from a counter; a warp that holds an item first loads everything that does not depend
+// on the solution (row bounds, indices, values, right-hand side, reciprocal diagonal) and only
+// then looks at the x entries it needs.  x (and the blocks' right-hand sides t) are pre-filled
+// with an "unset" bit pattern (all ones, a NaN no computation produces), so an entry IS its own
+// ready flag: a consumer re-reads it from L2 until it is set - one L2 round trip per dependency
+// level (~0.15 us) instead of a kernel boundary plus a chain of dependent HBM loads (~7.5 us).
+// Items are claimed in dependency order and only by running warps, so every wait is for an
+// item that a running warp already holds: no deadlock, whatever part of the grid is resident
+// (several subdomains' solves share the GPU).  Waits are bounded all the same: on expiry the
+// abort word is raised, every wait falls through, and the host reports the failure.
+// Summation order per row is the one of the level kernels above (same results bit for bit).
+// =============================================================================
+constexpr unsigned long long kTrsUnset = 0xffffffffffffffffull;
+
+__device__ __forceinline__ double ld_l2(const double *p)
+{
+    double v;
+    asm volatile("ld.relaxed.gpu.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_l2(double *p, double v)
+{
+    asm volatile("st.relaxed.gpu.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+__device__ __forceinline__ bool trs_unset(double v)
+{
+    return (unsigned long long)__double_as_longlong(v) == kTrsUnset;
+}
+// the value at p once it has been produced (0 after an abort)
+__device__ __forceinline__ double trs_wait(const double *p, volatile int32_t *abort_word)
+{
+    double v = ld_l2(p);
+    unsigned int spins = 0;
+    while (trs_unset(v)) {
+        __nanosleep(20);
+        if ((++spins & 4095u) == 0) {
+            if (*abort_word != 0) return 0.0;
+            if (spins > (1u << 25)) {   // seconds: something is wrong - stop everybody
+                atomicExch((int32_t *)abort_word, 1);
+                return 0.0;
+            }
+        }
+        v = ld_l2(p);
+    }
+    return v;
+}
+
+__global__ void __launch_bounds__(kBlock)
+    trs_prepare_kernel(int32_t n, double *__restrict__ x, int32_t nt, double *__restrict__ t,
+                       int32_t *counter, const int32_t *stop)
+{
+    if (stop != nullptr && *stop != 0) return;
+    const double unset = __longlong_as_double((long long)kTrsUnset);
+    const int64_t stride = (int64_t)gridDim.x * kBlock;
+    for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += stride) x[i] = unset;
+    for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < nt; i += stride) t[i] = unset;
+    if (blockIdx.x == 0 && threadIdx.x == 0) counter[0] = 0;
+}
+
+struct TrsFlowArgs {
+    int32_t num_items;
+    const int4 *items;
+    int32_t *counter;
+    const int32_t *order, *prp, *ci;
+    const double *v, *pinv;
+    const int32_t *crp, *cci;
+    const double *cv, *dinv;
+    const int32_t *blk_pos0, *blk_nb, *blk_ord0;
+    const int64_t *blk_off;
+    double *t;
+};
+
+// sum over entries [k0, k1) of val[k] * X[col[k]] with the lanes of a warp striding over the
+// entries, 4 gathers per lane in flight - the association of trs_row above
+__device__ __forceinline__ double trs_gather_row(int32_t k0, int32_t k1,
+                                                 const int32_t *__restrict__ col,
+                                                 const double *__restrict__ val, const double *X,
+                                                 int lane, volatile int32_t *abort_word)
+{
+    double s = 0.0;
+    for (int32_t k = k0 + lane; k < k1; k += 128) {
+        int32_t c[4];
+        double vv[4], xv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int32_t kk = k + 32 * u;
+            c[u] = kk < k1 ? col[kk] : -1;
+            vv[u] = kk < k1 ? val[kk] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) xv[u] = c[u] >= 0 ? ld_l2(X + c[u]) : 0.0;
+        double t[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (c[u] >= 0 && trs_unset(xv[u])) xv[u] = trs_wait(X + c[u], abort_word);
+            t[u] = c[u] >= 0 ? vv[u] * xv[u] : 0.0;
+        }
+        s += (t[0] + t[1]) + (t[2] + t[3]);
+    }
+    return warp_sum(s);
+}
+
+__global__ void __launch_bounds__(kBlock)
+    trs_flow_kernel(TrsFlowArgs A, const double *__restrict__ b, double *x, const int32_t *stop)
+{
+    if (stop != nullptr && *stop != 0) return;
+    const int lane = threadIdx.x & 31;
+    volatile int32_t *abort_word = A.counter + 1;
+    while (true) {
+        int32_t idx = 0;
+        if (lane == 0) idx = atomicAdd(A.counter, 1);
+        idx = __shfl_sync(0xffffffffu, idx, 0);
+        if (idx >= A.num_items) break;
+        const int4 it = __ldg(A.items + idx);
+        if (it.x == 0) {
+            // <= 32 short rows of one level, a lane each
+            if (lane < it.z) {
+                const int32_t pos = it.y + lane;
+                const int32_t row = A.order[pos];
+                const int32_t k0 = A.prp[pos], k1 = A.prp[pos + 1];
+                const double rhs = b[row], d = A.pinv[pos];
+                double s = 0.0;
+                for (int32_t k = k0; k < k1; ++k) {
+                    const int32_t c = A.ci[k];
+                    const double vv = A.v[k];
+                    s += vv * trs_wait(x + c, abort_word);
+                }
+                st_l2(x + row, (rhs - s) * d);
+            }
+        } else if (it.x == 1) {
+            const int32_t pos = it.y;
+            const int32_t row = A.order[pos];
+            const int32_t k0 = A.prp[pos], k1 = A.prp[pos + 1];
+            const double rhs = b[row], d = A.pinv[pos];
+            const double s = trs_gather_row(k0, k1, A.ci, A.v, x, lane, abort_word);
+            if (lane == 0) st_l2(x + row, (rhs - s) * d);
+        } else if (it.x == 2) {
+            // right-hand side of a block row: t = b - (entries outside the block) . x
+            const int32_t pos = it.y;
+            const int32_t k0 = A.crp[pos], k1 = A.crp[pos + 1];
+            const double rhs = b[A.order[pos]];
+            const double s = trs_gather_row(k0, k1, A.cci, A.cv, x, lane, abort_word);
+            if (lane == 0) st_l2(A.t + it.z, rhs - s);
+        } else {
+            // row r of x_K = Dinv_K t_K (Dinv row-major, lower triangle)
+            const int32_t blk = it.y, r = it.z;
+            const int32_t nb = A.blk_nb[blk];
+            const double *drow = A.dinv + A.blk_off[blk] + (size_t)r * nb;
+            const double *tk = A.t + A.blk_ord0[blk];
+            const int32_t row = A.order[A.blk_pos0[blk] + r];
+            double dv[kTrsBlock / 32];
+#pragma unroll
+            for (int jj = 0; jj < kTrsBlock / 32; ++jj) {
+                const int j = lane + 32 * jj;
+                dv[jj] = j <= r ? drow[j] : 0.0;
+            }
+            double acc = 0.0;
+#pragma unroll
+            for (int jj = 0; jj < kTrsBlock / 32; ++jj) {
+                const int j = lane + 32 * jj;
+                if (j <= r) acc += dv[jj] * trs_wait(tk + j, abort_word);
+            }
+            acc = warp_sum(acc);
+            if (lane == 0) st_l2(x + row, acc);
+        }
+    }
+}
+
+void TrsPlan::solve_flow(const double *b, double *x, const int32_t *stop)
+{
+    ctx_.use();
+    if (n_ == 0) return;
+    SCHWZ_REQUIRE(b != x, "triangular solve: right-hand side and solution must not alias");
+    static const int ctas_per_sm = [] {
+        const char *e = std::getenv("SCHWZ_B200_TRS_CTAS_PER_SM");
+        const int v = e ? std::atoi(e) : 0;
+        return v > 0 ? v : 4;
+    }();
+    const int fill_grid = (int)std::max<int64_t>(
+        1, std::min<int64_t>(((int64_t)n_ + kBlock - 1) / kBlock, ctx_.vec_grid()));
+    trs_prepare_kernel<<<fill_grid, kBlock, 0, ctx_.stream>>>(n_, x, num_chain_rows_, t_, counter_,
+                                                             stop);
+    TrsFlowArgs A;
+    A.num_items = num_items_;
+    A.items = reinterpret_cast<const int4 *>(items_);
+    A.counter = counter_;
+    A.order = order_;
+    A.prp = rp_;
+    A.ci = ci_;
+    A.v = v_;
+    A.pinv = inv_diag_;
+    A.crp = chain_rp_;
+    A.cci = chain_ci_;
+    A.cv = chain_v_;
+    A.dinv = dinv_;
+    A.blk_pos0 = blk_pos0_;
+    A.blk_nb = blk_nb_;
+    A.blk_ord0 = blk_ord0_;
+    A.blk_off = blk_dinv_off_;
+    A.t = t_;
+    const int grid = std::max(1, std::min((num_items_ + kTrsWarps - 1) / kTrsWarps,
+                                          ctx_.num_sms * ctas_per_sm));
+    trs_flow_kernel<<<grid, kBlock, 0, ctx_.stream>>>(A, b, x, stop);
+    SCHWZ_CUDA(cudaGetLastError());
+    count_launch(2);
+}
+
+int32_t TrsPlan::error()
+{
+    int32_t e = 0;
+    ctx_.use();
+    SCHWZ_CUDA(cudaMemcpyAsync(&e, counter_ + 1, sizeof(e), cudaMemcpyDeviceToHost, ctx_.stream));
+    SCHWZ_CUDA(cudaStreamSynchronize(ctx_.stream));
+    return e;
+}
+
+void TrsPlan::solve(const double *b, double *x, const int32_t *stop)
+{
+    // SCHWZ_B200_TRS_LEVELS=1: the level-per-launch graph (A/B measurements)
+    const char *e = std::getenv("SCHWZ_B200_TRS_LEVELS");
+    if (e && e[0] == '1') solve_levels(b, x, stop);
+    else solve_flow(b, x, stop);
 }
 
 }  // namespace schwz_b200

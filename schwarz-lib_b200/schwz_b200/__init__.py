@@ -599,6 +599,11 @@ class Trs:
         _chk(load().schwz_b200_trs_levels(self.h, C.byref(n)))
         return n.value
 
+    def error(self):
+        n = C.c_int32(0)
+        _chk(load().schwz_b200_trs_error(self.h, C.byref(n)))
+        return n.value
+
 
 class Comm:
     @staticmethod

@@ -3,7 +3,11 @@ one 264 192-row subdomain, nested-dissection Cholesky, nnz(L) = 7.9 M): one L so
 U = L^T solve, (a) alone on the GPU and (b) S solves side by side on S streams (the
 oversubscribed regime of cfg5: 8 subdomains per GPU on 8 GPUs, 64 on one).
 
-    python tools/prof_trs.py [S=16] [reps=20]
+    python tools/prof_trs.py [S=16] [reps=20] [ilu]
+
+SCHWZ_B200_TRS_LEVELS=1 selects the level-per-launch graph (round 1), default is the
+dependency-driven one-kernel solve.  With a third argument "ilu": the ILU(0) factors of a
+cfg2 strip (8192 x 1026 grid, natural order: ~9 200 wavefront levels) instead.
 """
 import os
 import sys
@@ -18,15 +22,29 @@ import schwz_b200 as S
 
 nsub = int(sys.argv[1]) if len(sys.argv) > 1 else 16
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 20
-n, P = 4096, 64
-setup = S.Setup(("laplacian2d", n), P, part=S.partition_regular2d(n * n, P))
-rp, ci, v = setup.local_matrix(9)
-rows = len(rp) - 1
-perm = S.nd_ordering(rp, ci)
-Lrp, Lci, Lv = S.host_cholesky(rp, ci, v, perm)
-U = sp.csr_matrix((Lv, Lci, Lrp), shape=(rows, rows)).T.tocsr()
-U.sort_indices()
-Urp, Uci, Uv = U.indptr.astype(np.int32), U.indices.astype(np.int32), U.data
+ilu = len(sys.argv) > 3 and sys.argv[3] == "ilu"
+if ilu:
+    # ILU(0) of the 5-pt Laplacian keeps the pattern of tril / triu; the values do not matter
+    # for the timing, a diagonally dominant pair with that pattern is used
+    n, P = 8192, 8
+    setup = S.Setup(("laplacian2d", n), P)
+    rp, ci, v = setup.local_matrix(1)
+    rows = len(rp) - 1
+    A = sp.csr_matrix((v, ci, rp), shape=(rows, rows))
+    Lm = sp.tril(A).tocsr(); Lm.sort_indices()
+    Um = sp.triu(A).tocsr(); Um.sort_indices()
+    Lrp, Lci, Lv = Lm.indptr.astype(np.int32), Lm.indices.astype(np.int32), Lm.data
+    Urp, Uci, Uv = Um.indptr.astype(np.int32), Um.indices.astype(np.int32), Um.data
+else:
+    n, P = 4096, 64
+    setup = S.Setup(("laplacian2d", n), P, part=S.partition_regular2d(n * n, P))
+    rp, ci, v = setup.local_matrix(9)
+    rows = len(rp) - 1
+    perm = S.nd_ordering(rp, ci)
+    Lrp, Lci, Lv = S.host_cholesky(rp, ci, v, perm)
+    U = sp.csr_matrix((Lv, Lci, Lrp), shape=(rows, rows)).T.tocsr()
+    U.sort_indices()
+    Urp, Uci, Uv = U.indptr.astype(np.int32), U.indices.astype(np.int32), U.data
 ctxs = [S.Context(0) for _ in range(nsub)]
 plans = []
 b = np.random.default_rng(0).standard_normal(rows)
@@ -38,13 +56,16 @@ c, tl, tu, db, dy, dz = plans[0]
 tl.solve(db, dy); tu.solve(dy, dz); c.sync()
 z = c.to_host(dz, rows)
 Lm = sp.csr_matrix((Lv, Lci, Lrp), shape=(rows, rows))
-print("residual |L L^T z - b| / |b| = %.2e, levels %d" % (np.linalg.norm(Lm @ (Lm.T @ z) - b) / np.linalg.norm(b), tl.levels()))
+Um = sp.csr_matrix((Uv, Uci, Urp), shape=(rows, rows))
+print("residual |L U z - b| / |b| = %.2e, levels %d, error words %d %d, mode %s"
+      % (np.linalg.norm(Lm @ (Um @ z) - b) / np.linalg.norm(b), tl.levels(), tl.error(), tu.error(),
+         "levels" if os.environ.get("SCHWZ_B200_TRS_LEVELS") == "1" else "one-kernel"))
 # (a) alone
 c.timer_start()
 for _ in range(reps):
     tl.solve(db, dy); tu.solve(dy, dz)
 ms = c.timer_stop() / reps
-byts = 2 * (12 * int(Lrp[-1]) + 20 * rows)
+byts = 12 * (int(Lrp[-1]) + int(Urp[-1])) + 2 * 20 * rows
 print("alone: L + U solve %.1f us, %.1f GB/s algorithmic" % (ms * 1e3, byts / ms / 1e6))
 # (b) nsub side by side
 for (c, tl, tu, db, dy, dz) in plans:
