@@ -15,6 +15,10 @@
 
 namespace schwz_b200 {
 
+// SCHWZ_B200_GMRES_MGS=1: modified Gram-Schmidt (Ginkgo's variant, k + 2 dependent reductions
+// per Arnoldi step) in the one-CTA GMRES instead of CGS2 (3 barriers per step)
+bool g_gmres_cgs2 = true;
+
 constexpr int kSmallMaxWarps = 32;
 constexpr int kSmallBuf = 2 * kSmallMaxWarps + 2;   // doubles of reduction scratch
 
@@ -177,7 +181,7 @@ __global__ void __launch_bounds__(kSmallThreads, 1)
                        const double *__restrict__ v_g, const double *__restrict__ b, double *x,
                        double *V, int32_t m, int32_t max_iters, double tol, double *resnorm_out,
                        double *r0_out, int32_t *total_out, int basis_in_smem, int matrix_in_smem,
-                       const int32_t *outer_stop)
+                       const int32_t *outer_stop, int cgs2)
 {
     extern __shared__ __align__(16) double sm[];
     int phase = 0;
@@ -191,7 +195,8 @@ __global__ void __launch_bounds__(kSmallThreads, 1)
     double *g = sn + m;                           // m+1
     double *y = g + m + 1;                        // m
     double *buf = y + m;                          // kSmallBuf
-    double *tail = buf + kSmallBuf;
+    double *hbuf = buf + kSmallBuf;               // m + 1: the projections of one CGS pass
+    double *tail = hbuf + m + 1;
     if (basis_in_smem) {
         V = tail;                                 // (m+1)*n
         tail += (size_t)(m + 1) * n;
@@ -272,13 +277,42 @@ __global__ void __launch_bounds__(kSmallThreads, 1)
             w[i] = acc;
         }
         double *col = H + (size_t)k * (m + 1);
-        for (int i = 0; i <= k; ++i) {   // modified Gram-Schmidt
-            const double *vi = V + (size_t)i * n;
-            double part = 0.0;
-            for (int32_t j = t; j < n; j += kSmallThreads) part += w[j] * vi[j];
-            const double h = cta_sum<kSmallThreads>(part, buf, phase);
-            if (t == 0) col[i] = h;
-            for (int32_t j = t; j < n; j += kSmallThreads) w[j] += (-h) * vi[j];
+        if (cgs2) {
+            // Classical Gram-Schmidt with re-orthogonalisation: the k + 1 projections of a pass
+            // are independent, so the warps take them side by side (a warp sums one whole dot
+            // product: no CTA-wide reduction) and ONE barrier ends the pass, against k + 1
+            // dependent CTA reductions for the modified variant below.  Two passes keep the
+            // basis orthogonal to working precision ("twice is enough"); the Hessenberg column
+            // is the sum of both.
+            constexpr int NW = kSmallThreads / 32;
+            const int lane = t & 31, wid = t >> 5;
+            __syncthreads();   // w complete
+            for (int pass = 0; pass < 2; ++pass) {
+                for (int i = wid; i <= k; i += NW) {
+                    const double *vi = V + (size_t)i * n;
+                    double part = 0.0;
+                    for (int32_t j = lane; j < n; j += 32) part += w[j] * vi[j];
+                    part = warp_sum(part);
+                    if (lane == 0) hbuf[i] = part;
+                }
+                __syncthreads();
+                for (int32_t j = t; j < n; j += kSmallThreads) {
+                    double acc = w[j];
+                    for (int i = 0; i <= k; ++i) acc += (-hbuf[i]) * V[(size_t)i * n + j];
+                    w[j] = acc;
+                }
+                if (t <= k) col[t] = pass == 0 ? hbuf[t] : col[t] + hbuf[t];
+                __syncthreads();
+            }
+        } else {
+            for (int i = 0; i <= k; ++i) {   // modified Gram-Schmidt
+                const double *vi = V + (size_t)i * n;
+                double part = 0.0;
+                for (int32_t j = t; j < n; j += kSmallThreads) part += w[j] * vi[j];
+                const double h = cta_sum<kSmallThreads>(part, buf, phase);
+                if (t == 0) col[i] = h;
+                for (int32_t j = t; j < n; j += kSmallThreads) w[j] += (-h) * vi[j];
+            }
         }
         double part = 0.0;
         for (int32_t j = t; j < n; j += kSmallThreads) part += w[j] * w[j];
@@ -322,7 +356,7 @@ __global__ void __launch_bounds__(kSmallThreads, 1)
 
 static size_t gmres_small_smem(int64_t n, int m, bool basis, int64_t nnz_in_smem = -1)
 {
-    size_t bytes = ((size_t)n + (size_t)(m + 1) * m + 4 * (size_t)m + 1 + kSmallBuf + 8 +
+    size_t bytes = ((size_t)n + (size_t)(m + 1) * m + 5 * (size_t)m + 2 + kSmallBuf + 8 +
                     (basis ? (size_t)(m + 1) * n : 0)) * sizeof(double);
     if (nnz_in_smem >= 0) bytes += 12 * (size_t)nnz_in_smem + 4 * ((size_t)n + 1) + 16;
     return bytes;
@@ -352,7 +386,7 @@ void launch_gmres_small(const Ctx &ctx, const DeviceCsr &A, const double *b, dou
                                                               : gmres_small_kernel<1024>;
     k<<<1, th, gmres_small_smem(A.nrows, m, basis, matrix ? A.nnz : -1), ctx.stream>>>(
         A.nrows, A.rp, A.ci, A.v, b, x, V, m, max_iters, tol, resnorm_out, r0_out, total_out,
-        basis ? 1 : 0, matrix ? 1 : 0, outer_stop);
+        basis ? 1 : 0, matrix ? 1 : 0, outer_stop, g_gmres_cgs2 ? 1 : 0);
     SCHWZ_CUDA(cudaGetLastError());
     count_launch();
 }

@@ -902,6 +902,25 @@ TrsPlan::TrsPlan(const Ctx &ctx, int32_t n, const int32_t *rp, const int32_t *ci
     // waits for items before it: the wide levels in level order (a chunk of <= 32 short rows
     // for the lanes of a warp, or one row per warp), then per block its right-hand-side rows
     // followed by the rows of the explicit inverse ------------------------------------------
+    // Every item also names ONE entry to watch before it looks at anything else: the
+    // dependency that sits latest in the item order (entries become ready roughly in that
+    // order).  A single lane polls that entry; only then do the lanes gather, re-checking each
+    // value - thousands of waiting warps otherwise poll with every lane and saturate L2.
+    std::vector<int32_t> pos_of((size_t)n, 0);
+    for (int32_t i = 0; i < n; ++i) pos_of[order[i]] = i;
+    auto latest_dep = [&](int32_t pos) {   // row id of the latest dependency of position pos
+        const int32_t row = order[pos];
+        int32_t best = -1, best_pos = -1;
+        for (int32_t k = rp[row]; k < rp[row + 1]; ++k) {
+            const int32_t c = ci[k];
+            if (c == row || !(upper ? c > row : c < row)) continue;
+            if (pos_of[c] > best_pos) {
+                best_pos = pos_of[c];
+                best = c;
+            }
+        }
+        return std::make_pair(best, best_pos);
+    };
     std::vector<Item> items;
     std::vector<int32_t> bpos0, bnb, bord0;
     std::vector<int64_t> boff;
@@ -912,9 +931,20 @@ TrsPlan::TrsPlan(const Ctx &ctx, int32_t n, const int32_t *rp, const int32_t *ci
             int64_t lnnz = 0;
             for (int32_t i = p0; i < p1; ++i) lnnz += rp[order[i] + 1] - rp[order[i]] - 1;
             if (lnnz <= 8 * (int64_t)(p1 - p0)) {
-                for (int32_t q = p0; q < p1; q += 32) items.push_back({0, q, std::min(32, p1 - q), 0});
+                for (int32_t q = p0; q < p1; q += 32) {
+                    const int32_t cnt = std::min(32, p1 - q);
+                    int32_t gate = -1, gate_pos = -1;
+                    for (int32_t i = 0; i < cnt; ++i) {
+                        auto d = latest_dep(q + i);
+                        if (d.second > gate_pos) {
+                            gate_pos = d.second;
+                            gate = d.first;
+                        }
+                    }
+                    items.push_back({0, q, cnt, gate});
+                }
             } else {
-                for (int32_t q = p0; q < p1; ++q) items.push_back({1, q, 0, 0});
+                for (int32_t q = p0; q < p1; ++q) items.push_back({1, q, 0, latest_dep(q).first});
             }
         } else {
             const int32_t blk = (int32_t)bpos0.size();
@@ -922,7 +952,22 @@ TrsPlan::TrsPlan(const Ctx &ctx, int32_t n, const int32_t *rp, const int32_t *ci
             bnb.push_back(sg.b);
             bord0.push_back(ord);
             boff.push_back(sg.dinv_off);
-            for (int32_t i = 0; i < sg.b; ++i) items.push_back({2, sg.a + i, ord + i, 0});
+            for (int32_t i = 0; i < sg.b; ++i) {
+                // latest dependency OUTSIDE the block (inside ones are folded into Dinv)
+                const int32_t row = order[sg.a + i];
+                int32_t gate = -1, gate_pos = -1;
+                for (int32_t k = rp[row]; k < rp[row + 1]; ++k) {
+                    const int32_t c = ci[k];
+                    if (c == row || !(upper ? c > row : c < row)) continue;
+                    const int32_t pc = pos_of[c];
+                    if (pc >= sg.a && pc < sg.a + sg.b) continue;
+                    if (pc > gate_pos) {
+                        gate_pos = pc;
+                        gate = c;
+                    }
+                }
+                items.push_back({2, sg.a + i, ord + i, gate});
+            }
             for (int32_t i = 0; i < sg.b; ++i) items.push_back({3, blk, i, 0});
             ord += sg.b;
         }
@@ -1048,10 +1093,9 @@ __device__ __forceinline__ double trs_wait(const double *p, volatile int32_t *ab
     double v = ld_l2(p);
     unsigned int spins = 0;
     while (trs_unset(v)) {
-        __nanosleep(20);
         if ((++spins & 4095u) == 0) {
             if (*abort_word != 0) return 0.0;
-            if (spins > (1u << 25)) {   // seconds: something is wrong - stop everybody
+            if (spins > (1u << 26)) {   // seconds: something is wrong - stop everybody
                 atomicExch((int32_t *)abort_word, 1);
                 return 0.0;
             }
@@ -1059,6 +1103,12 @@ __device__ __forceinline__ double trs_wait(const double *p, volatile int32_t *ab
         v = ld_l2(p);
     }
     return v;
+}
+// one lane watches the item's latest dependency, the warp goes on when it is there
+__device__ __forceinline__ void trs_gate(const double *p, int lane, volatile int32_t *abort_word)
+{
+    if (lane == 0) (void)trs_wait(p, abort_word);
+    __syncwarp();
 }
 
 __global__ void __launch_bounds__(kBlock)
@@ -1130,11 +1180,17 @@ __global__ void __launch_bounds__(kBlock)
         const int4 it = __ldg(A.items + idx);
         if (it.x == 0) {
             // <= 32 short rows of one level, a lane each
+            int32_t pos = it.y + lane, row = 0, k0 = 0, k1 = 0;
+            double rhs = 0.0, d = 0.0;
+            if (lane < it.z) {   // everything that does not depend on x first
+                row = A.order[pos];
+                k0 = A.prp[pos];
+                k1 = A.prp[pos + 1];
+                rhs = b[row];
+                d = A.pinv[pos];
+            }
+            if (it.w >= 0) trs_gate(x + it.w, lane, abort_word);
             if (lane < it.z) {
-                const int32_t pos = it.y + lane;
-                const int32_t row = A.order[pos];
-                const int32_t k0 = A.prp[pos], k1 = A.prp[pos + 1];
-                const double rhs = b[row], d = A.pinv[pos];
                 double s = 0.0;
                 for (int32_t k = k0; k < k1; ++k) {
                     const int32_t c = A.ci[k];
@@ -1148,6 +1204,7 @@ __global__ void __launch_bounds__(kBlock)
             const int32_t row = A.order[pos];
             const int32_t k0 = A.prp[pos], k1 = A.prp[pos + 1];
             const double rhs = b[row], d = A.pinv[pos];
+            if (it.w >= 0) trs_gate(x + it.w, lane, abort_word);
             const double s = trs_gather_row(k0, k1, A.ci, A.v, x, lane, abort_word);
             if (lane == 0) st_l2(x + row, (rhs - s) * d);
         } else if (it.x == 2) {
@@ -1155,6 +1212,7 @@ __global__ void __launch_bounds__(kBlock)
             const int32_t pos = it.y;
             const int32_t k0 = A.crp[pos], k1 = A.crp[pos + 1];
             const double rhs = b[A.order[pos]];
+            if (it.w >= 0) trs_gate(x + it.w, lane, abort_word);
             const double s = trs_gather_row(k0, k1, A.cci, A.cv, x, lane, abort_word);
             if (lane == 0) st_l2(A.t + it.z, rhs - s);
         } else {
@@ -1170,6 +1228,7 @@ __global__ void __launch_bounds__(kBlock)
                 const int j = lane + 32 * jj;
                 dv[jj] = j <= r ? drow[j] : 0.0;
             }
+            trs_gate(tk + r, lane, abort_word);   // the row's own right-hand side
             double acc = 0.0;
 #pragma unroll
             for (int jj = 0; jj < kTrsBlock / 32; ++jj) {
@@ -1190,7 +1249,7 @@ void TrsPlan::solve_flow(const double *b, double *x, const int32_t *stop)
     static const int ctas_per_sm = [] {
         const char *e = std::getenv("SCHWZ_B200_TRS_CTAS_PER_SM");
         const int v = e ? std::atoi(e) : 0;
-        return v > 0 ? v : 4;
+        return v > 0 ? v : 1;
     }();
     const int fill_grid = (int)std::max<int64_t>(
         1, std::min<int64_t>(((int64_t)n_ + kBlock - 1) / kBlock, ctx_.vec_grid()));
