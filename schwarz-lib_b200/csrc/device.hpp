@@ -74,9 +74,16 @@ struct DeviceCsr {
     int32_t *blk_row = nullptr;
     bool has_long_row = false;
     int32_t rows_per_tile = kBlock;
+    // Compact column stream of the pipelined SpMV: when the columns of every row tile span
+    // less than 2^16 (stencil / banded local matrices: a 256-row tile of a cfg2 strip spans
+    // 16 640 columns) the kernel reads 16-bit offsets from the tile's first column instead of
+    // 32-bit indices: 10 instead of 12 B per non-zero from HBM.  ci stays for everybody else.
+    uint16_t *ci16 = nullptr;
+    int32_t *tile_col0 = nullptr;
     ~DeviceCsr();
 };
 
+extern bool g_spmv_col16;   // SCHWZ_B200_SPMV_COL32=1 turns the 16-bit column stream off
 extern bool g_force_simple_spmv;
 extern int g_spmv_variant;
 DeviceCsr *csr_upload(const Ctx &ctx, int32_t nrows, int32_t ncols, const int32_t *rp,

@@ -15,6 +15,7 @@
 namespace schwz_b200 {
 
 std::atomic<int64_t> g_launches{0};
+bool g_spmv_col16 = true;           // SCHWZ_B200_SPMV_COL32=1: 32-bit column indices (A/B)
 bool g_force_simple_spmv = false;   // SCHWZ_B200_SIMPLE_SPMV=1: one-shot kernel (A/B measurements)
 int g_spmv_variant = 1;             // SCHWZ_B200_SPMV_VARIANT: launch shape of the pipelined kernel
 
@@ -55,6 +56,8 @@ DeviceCsr::~DeviceCsr()
     ctx->release(ci);
     ctx->release(v);
     ctx->release(blk_row);
+    ctx->release(ci16);
+    ctx->release(tile_col0);
 }
 
 DeviceCsr *csr_upload(const Ctx &ctx, int32_t nrows, int32_t ncols, const int32_t *rp,
@@ -103,7 +106,7 @@ DeviceCsr *csr_upload(const Ctx &ctx, int32_t nrows, int32_t ncols, const int32_
     // every array is padded by 8 elements past its end.
     auto upload_padded = [&](auto *host, size_t n, auto zero) {
         using T = decltype(zero);
-        T *d = ctx.alloc_zero<T>(n + 8);
+        T *d = ctx.alloc_zero<T>(n + 16);
         if (n) SCHWZ_CUDA(cudaMemcpyAsync(d, host, n * sizeof(T), cudaMemcpyHostToDevice, ctx.stream));
         SCHWZ_CUDA(cudaStreamSynchronize(ctx.stream));
         return d;
@@ -113,6 +116,34 @@ DeviceCsr *csr_upload(const Ctx &ctx, int32_t nrows, int32_t ncols, const int32_
     A->ci = upload_padded(ci, (size_t)A->nnz, int32_t(0));
     A->v = upload_padded(v, (size_t)A->nnz, double(0));
     A->blk_row = ctx.upload(blk.data(), blk.size());
+    if (g_spmv_col16 && !A->has_long_row && A->nnz > 0) {
+        std::vector<int32_t> col0((size_t)A->nblocks, 0);
+        bool fits = true;
+        for (int32_t b = 0; b < A->nblocks && fits; ++b) {
+            const int32_t k0 = rp[blk[b]], k1 = rp[blk[b + 1]];
+            if (k0 == k1) continue;
+            int32_t lo = ci[k0], hi = ci[k0];
+            for (int32_t k = k0 + 1; k < k1; ++k) {
+                lo = std::min(lo, ci[k]);
+                hi = std::max(hi, ci[k]);
+            }
+            col0[b] = lo;
+            fits = (int64_t)hi - lo < 65536;
+        }
+        if (fits) {
+            std::vector<uint16_t> c16((size_t)A->nnz);
+            for (int32_t b = 0; b < A->nblocks; ++b)
+                for (int32_t k = rp[blk[b]]; k < rp[blk[b + 1]]; ++k)
+                    c16[k] = (uint16_t)(ci[k] - col0[b]);
+            // 16-byte granules of 8 entries: pad by 16
+            uint16_t *d = ctx.alloc_zero<uint16_t>((size_t)A->nnz + 16);
+            SCHWZ_CUDA(cudaMemcpyAsync(d, c16.data(), c16.size() * sizeof(uint16_t),
+                                       cudaMemcpyHostToDevice, ctx.stream));
+            SCHWZ_CUDA(cudaStreamSynchronize(ctx.stream));
+            A->ci16 = d;
+            A->tile_col0 = ctx.upload(col0.data(), col0.size());
+        }
+    }
     return A;
 }
 
@@ -225,15 +256,15 @@ __global__ void __launch_bounds__(kBlock)
 constexpr int kSpmvChunk = 6;     // non-zeros of a row gathered per round
 constexpr int kSpmvThreads = kBlock + 32;   // 8 consumer warps + 1 producer warp
 
-template <int RPT>
+template <int RPT, typename ColT>
 struct __align__(16) SpmvStage {
-    double val[kSpmvTile * RPT + 8];
-    int32_t col[kSpmvTile * RPT + 8];
+    double val[kSpmvTile * RPT + 16];
+    ColT col[kSpmvTile * RPT + 16];
     int32_t rp[kBlock * RPT + 8];
 };
-template <int RPT, int STAGES>
+template <int RPT, int STAGES, typename ColT>
 struct __align__(16) SpmvSmem {
-    SpmvStage<RPT> st[STAGES];
+    SpmvStage<RPT, ColT> st[STAGES];
     double warp_buf[kBlock / 32];
     unsigned long long full[STAGES], empty[STAGES];
     int last;
@@ -286,19 +317,22 @@ __device__ __forceinline__ void consumer_sync()
     asm volatile("bar.sync 1, %0;" ::"n"(kBlock) : "memory");
 }
 
-template <int EPI, int RPT, int STAGES, int CTAS>
+// ColT = int32_t: column indices as stored; uint16_t: offsets from tile_col0[tile]
+template <int EPI, int RPT, int STAGES, int CTAS, typename ColT>
 __global__ void __launch_bounds__(kSpmvThreads, CTAS)
     csr_spmv_tma_kernel(int32_t ntiles, const int32_t *__restrict__ blk_row,
-                        const int32_t *__restrict__ rp, const int32_t *__restrict__ ci,
+                        const int32_t *__restrict__ rp, const ColT *__restrict__ ci,
+                        const int32_t *__restrict__ tile_col0,
                         const double *__restrict__ v, const double *__restrict__ x, double alpha,
                         double beta, const double *y_in, double *y_out, const double *dot_with,
                         double *partials, unsigned int *ticket, double *result, int32_t red_rows,
                         const int32_t *stop)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    using Smem = SpmvSmem<RPT, STAGES>;
+    using Smem = SpmvSmem<RPT, STAGES, ColT>;
     Smem &S = *reinterpret_cast<Smem *>(smem_raw);
     if (stop != nullptr && *stop != 0) return;
+    constexpr int32_t G = 16 / (int)sizeof(ColT);   // entries per 16-byte granule of the col stream
 
     const int t = threadIdx.x;
     if (t == 0) {
@@ -320,14 +354,15 @@ __global__ void __launch_bounds__(kSpmvThreads, CTAS)
                 const int s = it % STAGES;
                 const int32_t r0 = blk_row[b], r1 = blk_row[b + 1];
                 const int32_t k0 = rp[r0], k1 = rp[r1];
-                const int32_t k0a = k0 & ~3, k1a = (k1 + 3) & ~3;       // 4-element granules
+                const int32_t k0a = k0 & ~(G - 1), k1a = (k1 + G - 1) & ~(G - 1);   // granules
                 const int32_t r0a = r0 & ~3, r1a = (r1 + 1 + 3) & ~3;
                 const uint32_t nv = (uint32_t)(k1a - k0a), nr = (uint32_t)(r1a - r0a);
                 mbar_wait(&S.empty[s], ((it / STAGES) & 1) ^ 1);
-                mbar_expect_tx(&S.full[s], nv * 12u + nr * 4u);
+                mbar_expect_tx(&S.full[s], nv * (8u + (uint32_t)sizeof(ColT)) + nr * 4u);
                 if (nv) {
                     bulk_g2s(S.st[s].val, v + k0a, nv * 8u, &S.full[s], policy);
-                    bulk_g2s(S.st[s].col, ci + k0a, nv * 4u, &S.full[s], policy);
+                    bulk_g2s(S.st[s].col, ci + k0a, nv * (uint32_t)sizeof(ColT), &S.full[s],
+                             policy);
                 }
                 bulk_g2s(S.st[s].rp, rp + r0a, nr * 4u, &S.full[s], policy);
             }
@@ -351,9 +386,11 @@ __global__ void __launch_bounds__(kSpmvThreads, CTAS)
         const int32_t r0 = blk_row[b];
         const int32_t nr = blk_row[b + 1] - r0;
         mbar_wait(&S.full[s], (it / STAGES) & 1);
-        const SpmvStage<RPT> &T = S.st[s];
+        const SpmvStage<RPT, ColT> &T = S.st[s];
         const int32_t *srp = T.rp + (r0 & 3);
-        const int32_t base = (srp[0] & ~3);   // first staged element
+        const int32_t base = (srp[0] & ~(G - 1));   // first staged element
+        const double *xt = x;
+        if (sizeof(ColT) == 2) xt += __ldg(tile_col0 + b);   // offsets count from the tile's column 0
         int32_t k[RPT], e[RPT];
         double acc[RPT];
         bool more = false;
@@ -377,7 +414,7 @@ __global__ void __launch_bounds__(kSpmvThreads, CTAS)
 #pragma unroll
                 for (int i = 0; i < kSpmvChunk; ++i)
                     if (k[j] + i < e[j]) {
-                        xv[j][i] = __ldg(x + T.col[k[j] + i]);
+                        xv[j][i] = __ldg(xt + T.col[k[j] + i]);
                         vv[j][i] = T.val[k[j] + i];
                     }
             more = false;
@@ -437,26 +474,43 @@ __global__ void __launch_bounds__(kSpmvThreads, CTAS)
     }
 }
 
+template <int EPI, int RPT, int STAGES, int CTAS, typename ColT>
+static void launch_spmv_tma_cols(const Ctx &ctx, const DeviceCsr &A, const ColT *cols, double alpha,
+                                 const double *x, double beta, const double *y_in, double *y_out,
+                                 const double *dot_with, double *result, int32_t red_rows,
+                                 const int32_t *stop)
+{
+    using Smem = SpmvSmem<RPT, STAGES, ColT>;
+    // per-device, set once; several host threads (bench_ras rank threads) may arrive together:
+    // setting the attribute twice is harmless, the flag is an atomic
+    static std::atomic<bool> configured[64];
+    if (!configured[ctx.device].load(std::memory_order_acquire)) {
+        SCHWZ_CUDA(cudaFuncSetAttribute(csr_spmv_tma_kernel<EPI, RPT, STAGES, CTAS, ColT>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)sizeof(Smem)));
+        configured[ctx.device].store(true, std::memory_order_release);
+    }
+    const int grid = std::min<int>(A.nblocks, ctx.num_sms * CTAS);
+    csr_spmv_tma_kernel<EPI, RPT, STAGES, CTAS, ColT>
+        <<<grid, kSpmvThreads, sizeof(Smem), ctx.stream>>>(
+            A.nblocks, A.blk_row, A.rp, cols, A.tile_col0, A.v, x, alpha, beta, y_in, y_out,
+            dot_with, ctx.partials, ctx.tickets + 0, result, red_rows, stop);
+}
+
 template <int EPI, int RPT, int STAGES, int CTAS>
 static void launch_spmv_tma_cfg(const Ctx &ctx, const DeviceCsr &A, double alpha, const double *x,
                                 double beta, const double *y_in, double *y_out,
                                 const double *dot_with, double *result, int32_t red_rows,
                                 const int32_t *stop)
 {
-    using Smem = SpmvSmem<RPT, STAGES>;
-    // per-device, set once; several host threads (bench_ras rank threads) may arrive together:
-    // setting the attribute twice is harmless, the flag is an atomic
-    static std::atomic<bool> configured[64];
-    if (!configured[ctx.device].load(std::memory_order_acquire)) {
-        SCHWZ_CUDA(cudaFuncSetAttribute(csr_spmv_tma_kernel<EPI, RPT, STAGES, CTAS>,
-                                        cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)sizeof(Smem)));
-        configured[ctx.device].store(true, std::memory_order_release);
-    }
-    const int grid = std::min<int>(A.nblocks, ctx.num_sms * CTAS);
-    csr_spmv_tma_kernel<EPI, RPT, STAGES, CTAS><<<grid, kSpmvThreads, sizeof(Smem), ctx.stream>>>(
-        A.nblocks, A.blk_row, A.rp, A.ci, A.v, x, alpha, beta, y_in, y_out, dot_with, ctx.partials,
-        ctx.tickets + 0, result, red_rows, stop);
+    if (A.ci16 != nullptr)
+        launch_spmv_tma_cols<EPI, RPT, STAGES, CTAS, uint16_t>(ctx, A, A.ci16, alpha, x, beta, y_in,
+                                                               y_out, dot_with, result, red_rows,
+                                                               stop);
+    else
+        launch_spmv_tma_cols<EPI, RPT, STAGES, CTAS, int32_t>(ctx, A, A.ci, alpha, x, beta, y_in,
+                                                              y_out, dot_with, result, red_rows,
+                                                              stop);
 }
 
 template <int EPI>
