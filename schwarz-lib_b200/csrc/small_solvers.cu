@@ -260,6 +260,117 @@ __global__ void __launch_bounds__(kSmallThreads, 1)
     double resnorm = begin_cycle();
     const double r0 = resnorm;
     int total = -1, k = 0;
+    // Givens update of Hessenberg column kk (entries 0..kk set, hn below the diagonal): the new
+    // implicit residual norm goes to buf[kSmallBuf - 1]
+    auto givens = [&](int kk, double hn) {
+        double *col = H + (size_t)kk * (m + 1);
+        col[kk + 1] = hn;
+        for (int i = 0; i < kk; ++i) {
+            const double tt = cs[i] * col[i] + sn[i] * col[i + 1];
+            col[i + 1] = -sn[i] * col[i] + cs[i] * col[i + 1];
+            col[i] = tt;
+        }
+        const double a = col[kk], c = col[kk + 1];
+        if (a == 0.0) {
+            cs[kk] = 0.0;
+            sn[kk] = 1.0;
+        } else {
+            const double sc = fabs(a) + fabs(c);
+            const double hyp = sc * sqrt((a / sc) * (a / sc) + (c / sc) * (c / sc));
+            cs[kk] = a / hyp;
+            sn[kk] = c / hyp;
+        }
+        col[kk] = cs[kk] * a + sn[kk] * c;
+        col[kk + 1] = 0.0;
+        g[kk + 1] = -sn[kk] * g[kk];
+        g[kk] = cs[kk] * g[kk];
+        buf[kSmallBuf - 1] = fabs(g[kk + 1]);
+    };
+    if (cgs2) {
+        // ---- CGS2 variant.  Per Arnoldi step: the Givens update of the PREVIOUS column (one
+        // thread, a chain of dependent fp64 operations) runs beside the SpMV of this step, the
+        // k + 1 projections of a Gram-Schmidt pass are taken by the warps side by side (a warp
+        // sums whole dot products with 4 independent partial sums: no CTA-wide reduction), one
+        // barrier ends a pass; two passes keep the basis orthogonal to working precision.
+        // Stopping rule, restart schedule and the quantities handed back are those of the
+        // modified variant below (Ginkgo's), the arithmetic inside a step is not.
+        constexpr int NW = kSmallThreads / 32;
+        const int lane = t & 31, wid = t >> 5;
+        bool pending = false;   // a Givens update (column k - 1) is still to be done
+        double hn_prev = 0.0;
+        while (true) {
+            // w = A V_k beside the pending Givens update (the last thread does that one and
+            // leaves the rows to the others); the stop test below needs its result
+            if (k < m) {
+                const double *vk = V + (size_t)k * n;
+                const int workers = pending ? kSmallThreads - 1 : kSmallThreads;
+                if (t < workers)
+                    for (int32_t i = t; i < n; i += workers) {
+                        double acc = 0.0;
+                        for (int32_t q = rp[i]; q < rp[i + 1]; ++q) acc += v[q] * vk[ci[q]];
+                        w[i] = acc;
+                    }
+            }
+            if (pending && t == kSmallThreads - 1) givens(k - 1, hn_prev);
+            __syncthreads();
+            if (pending) resnorm = buf[kSmallBuf - 1];
+            pending = false;
+            ++total;
+            if (total >= max_iters || resnorm < tol * r0) break;
+            if (k == m) {
+                update_x(k);
+                resnorm = begin_cycle();
+                k = 0;
+                const double *v0 = V;
+                for (int32_t i = t; i < n; i += kSmallThreads) {
+                    double acc = 0.0;
+                    for (int32_t q = rp[i]; q < rp[i + 1]; ++q) acc += v[q] * v0[ci[q]];
+                    w[i] = acc;
+                }
+                __syncthreads();
+            }
+            double *col = H + (size_t)k * (m + 1);
+            for (int pass = 0; pass < 2; ++pass) {
+                for (int i = wid; i <= k; i += NW) {
+                    const double *vi = V + (size_t)i * n;
+                    double p0 = 0.0, p1 = 0.0, p2 = 0.0, p3 = 0.0;
+                    int32_t j = lane;
+                    for (; j + 96 < n; j += 128) {
+                        p0 += w[j] * vi[j];
+                        p1 += w[j + 32] * vi[j + 32];
+                        p2 += w[j + 64] * vi[j + 64];
+                        p3 += w[j + 96] * vi[j + 96];
+                    }
+                    for (; j < n; j += 32) p0 += w[j] * vi[j];
+                    const double part = warp_sum((p0 + p1) + (p2 + p3));
+                    if (lane == 0) hbuf[i] = part;
+                }
+                __syncthreads();
+                for (int32_t j = t; j < n; j += kSmallThreads) {
+                    double a0 = w[j], a1 = 0.0;
+                    int i = 0;
+                    for (; i + 1 <= k; i += 2) {
+                        a0 += (-hbuf[i]) * V[(size_t)i * n + j];
+                        a1 += (-hbuf[i + 1]) * V[(size_t)(i + 1) * n + j];
+                    }
+                    if (i <= k) a0 += (-hbuf[i]) * V[(size_t)i * n + j];
+                    w[j] = a0 + a1;
+                }
+                if (t <= k) col[t] = pass == 0 ? hbuf[t] : col[t] + hbuf[t];
+                __syncthreads();
+            }
+            double part = 0.0;
+            for (int32_t j = t; j < n; j += kSmallThreads) part += w[j] * w[j];
+            const double hn = sqrt(cta_sum<kSmallThreads>(part, buf, phase));
+            const double inv = hn != 0.0 ? 1.0 / hn : 0.0;
+            double *vn = V + (size_t)(k + 1) * n;
+            for (int32_t j = t; j < n; j += kSmallThreads) vn[j] = w[j] * inv;
+            hn_prev = hn;
+            pending = true;
+            ++k;
+            __syncthreads();   // V_{k+1} complete (and visible when it lives in global memory)
+        }
+    } else
     while (true) {
         ++total;
         if (total >= max_iters || resnorm < tol * r0) break;
@@ -277,71 +388,20 @@ __global__ void __launch_bounds__(kSmallThreads, 1)
             w[i] = acc;
         }
         double *col = H + (size_t)k * (m + 1);
-        if (cgs2) {
-            // Classical Gram-Schmidt with re-orthogonalisation: the k + 1 projections of a pass
-            // are independent, so the warps take them side by side (a warp sums one whole dot
-            // product: no CTA-wide reduction) and ONE barrier ends the pass, against k + 1
-            // dependent CTA reductions for the modified variant below.  Two passes keep the
-            // basis orthogonal to working precision ("twice is enough"); the Hessenberg column
-            // is the sum of both.
-            constexpr int NW = kSmallThreads / 32;
-            const int lane = t & 31, wid = t >> 5;
-            __syncthreads();   // w complete
-            for (int pass = 0; pass < 2; ++pass) {
-                for (int i = wid; i <= k; i += NW) {
-                    const double *vi = V + (size_t)i * n;
-                    double part = 0.0;
-                    for (int32_t j = lane; j < n; j += 32) part += w[j] * vi[j];
-                    part = warp_sum(part);
-                    if (lane == 0) hbuf[i] = part;
-                }
-                __syncthreads();
-                for (int32_t j = t; j < n; j += kSmallThreads) {
-                    double acc = w[j];
-                    for (int i = 0; i <= k; ++i) acc += (-hbuf[i]) * V[(size_t)i * n + j];
-                    w[j] = acc;
-                }
-                if (t <= k) col[t] = pass == 0 ? hbuf[t] : col[t] + hbuf[t];
-                __syncthreads();
-            }
-        } else {
-            for (int i = 0; i <= k; ++i) {   // modified Gram-Schmidt
-                const double *vi = V + (size_t)i * n;
-                double part = 0.0;
-                for (int32_t j = t; j < n; j += kSmallThreads) part += w[j] * vi[j];
-                const double h = cta_sum<kSmallThreads>(part, buf, phase);
-                if (t == 0) col[i] = h;
-                for (int32_t j = t; j < n; j += kSmallThreads) w[j] += (-h) * vi[j];
-            }
+        for (int i = 0; i <= k; ++i) {   // modified Gram-Schmidt
+            const double *vi = V + (size_t)i * n;
+            double part = 0.0;
+            for (int32_t j = t; j < n; j += kSmallThreads) part += w[j] * vi[j];
+            const double h = cta_sum<kSmallThreads>(part, buf, phase);
+            if (t == 0) col[i] = h;
+            for (int32_t j = t; j < n; j += kSmallThreads) w[j] += (-h) * vi[j];
         }
         double part = 0.0;
         for (int32_t j = t; j < n; j += kSmallThreads) part += w[j] * w[j];
         const double hn = sqrt(cta_sum<kSmallThreads>(part, buf, phase));
         double *vn = V + (size_t)(k + 1) * n;
         for (int32_t j = t; j < n; j += kSmallThreads) vn[j] = hn != 0.0 ? w[j] / hn : 0.0;
-        if (t == 0) {
-            col[k + 1] = hn;
-            for (int i = 0; i < k; ++i) {
-                const double tt = cs[i] * col[i] + sn[i] * col[i + 1];
-                col[i + 1] = -sn[i] * col[i] + cs[i] * col[i + 1];
-                col[i] = tt;
-            }
-            const double a = col[k], c = col[k + 1];
-            if (a == 0.0) {
-                cs[k] = 0.0;
-                sn[k] = 1.0;
-            } else {
-                const double sc = fabs(a) + fabs(c);
-                const double hyp = sc * sqrt((a / sc) * (a / sc) + (c / sc) * (c / sc));
-                cs[k] = a / hyp;
-                sn[k] = c / hyp;
-            }
-            col[k] = cs[k] * a + sn[k] * c;
-            col[k + 1] = 0.0;
-            g[k + 1] = -sn[k] * g[k];
-            g[k] = cs[k] * g[k];
-            buf[kSmallBuf - 1] = fabs(g[k + 1]);
-        }
+        if (t == 0) givens(k, hn);
         __syncthreads();   // also makes V_{k+1} (global) visible to the whole CTA
         resnorm = buf[kSmallBuf - 1];
         ++k;

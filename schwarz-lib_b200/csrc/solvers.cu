@@ -1137,22 +1137,31 @@ struct TrsFlowArgs {
 };
 
 // sum over entries [k0, k1) of val[k] * X[col[k]] with the lanes of a warp striding over the
-// entries, 4 gathers per lane in flight - the association of trs_row above
+// entries, 4 gathers per lane in flight - the association of trs_row above.  The indices and
+// values of the next round are loaded before the x entries of this one are looked at, and a
+// lane only ever waits for an entry that is really still missing: whatever part of a long row
+// refers to rows solved long ago is summed up while the latest dependencies are still in work.
 __device__ __forceinline__ double trs_gather_row(int32_t k0, int32_t k1,
                                                  const int32_t *__restrict__ col,
                                                  const double *__restrict__ val, const double *X,
                                                  int lane, volatile int32_t *abort_word)
 {
     double s = 0.0;
-    for (int32_t k = k0 + lane; k < k1; k += 128) {
-        int32_t c[4];
-        double vv[4], xv[4];
+    int32_t c[4], cn[4];
+    double vv[4], vn[4], xv[4];
+    auto load_round = [&](int32_t k, int32_t *cc, double *vc) {
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const int32_t kk = k + 32 * u;
-            c[u] = kk < k1 ? col[kk] : -1;
-            vv[u] = kk < k1 ? val[kk] : 0.0;
+            cc[u] = kk < k1 ? __ldg(col + kk) : -1;
+            vc[u] = kk < k1 ? __ldg(val + kk) : 0.0;
         }
+    };
+    int32_t k = k0 + lane;
+    if (k < k1) load_round(k, c, vv);
+    for (; k < k1; k += 128) {
+        const bool more = k + 128 < k1;
+        if (more) load_round(k + 128, cn, vn);
 #pragma unroll
         for (int u = 0; u < 4; ++u) xv[u] = c[u] >= 0 ? ld_l2(X + c[u]) : 0.0;
         double t[4];
@@ -1162,6 +1171,13 @@ __device__ __forceinline__ double trs_gather_row(int32_t k0, int32_t k1,
             t[u] = c[u] >= 0 ? vv[u] * xv[u] : 0.0;
         }
         s += (t[0] + t[1]) + (t[2] + t[3]);
+        if (more) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                c[u] = cn[u];
+                vv[u] = vn[u];
+            }
+        }
     }
     return warp_sum(s);
 }
@@ -1172,27 +1188,41 @@ __global__ void __launch_bounds__(kBlock)
     if (stop != nullptr && *stop != 0) return;
     const int lane = threadIdx.x & 31;
     volatile int32_t *abort_word = A.counter + 1;
-    while (true) {
-        int32_t idx = 0;
-        if (lane == 0) idx = atomicAdd(A.counter, 1);
-        idx = __shfl_sync(0xffffffffu, idx, 0);
-        if (idx >= A.num_items) break;
+    // a warp always holds its current item and has the next one claimed: the claim and the
+    // item's descriptor travel while the current item is being worked on
+    int32_t idx = 0;
+    if (lane == 0) idx = atomicAdd(A.counter, 1);
+    idx = __shfl_sync(0xffffffffu, idx, 0);
+    while (idx < A.num_items) {
+        int32_t next = 0;
+        if (lane == 0) next = atomicAdd(A.counter, 1);
         const int4 it = __ldg(A.items + idx);
         if (it.x == 0) {
-            // <= 32 short rows of one level, a lane each
-            int32_t pos = it.y + lane, row = 0, k0 = 0, k1 = 0;
-            double rhs = 0.0, d = 0.0;
-            if (lane < it.z) {   // everything that does not depend on x first
+            // <= 32 short rows of one level, a lane each; everything that does not depend on
+            // x is fetched before the warp looks at its latest dependency
+            constexpr int kPre = 4;
+            int32_t row = 0, k0 = 0, k1 = 0, pc[kPre];
+            double rhs = 0.0, d = 0.0, pv[kPre];
+            if (lane < it.z) {
+                const int32_t pos = it.y + lane;
                 row = A.order[pos];
                 k0 = A.prp[pos];
                 k1 = A.prp[pos + 1];
                 rhs = b[row];
                 d = A.pinv[pos];
+#pragma unroll
+                for (int u = 0; u < kPre; ++u) {
+                    pc[u] = k0 + u < k1 ? __ldg(A.ci + k0 + u) : -1;
+                    pv[u] = k0 + u < k1 ? __ldg(A.v + k0 + u) : 0.0;
+                }
             }
             if (it.w >= 0) trs_gate(x + it.w, lane, abort_word);
             if (lane < it.z) {
                 double s = 0.0;
-                for (int32_t k = k0; k < k1; ++k) {
+#pragma unroll
+                for (int u = 0; u < kPre; ++u)
+                    if (pc[u] >= 0) s += pv[u] * trs_wait(x + pc[u], abort_word);
+                for (int32_t k = k0 + kPre; k < k1; ++k) {
                     const int32_t c = A.ci[k];
                     const double vv = A.v[k];
                     s += vv * trs_wait(x + c, abort_word);
@@ -1204,7 +1234,6 @@ __global__ void __launch_bounds__(kBlock)
             const int32_t row = A.order[pos];
             const int32_t k0 = A.prp[pos], k1 = A.prp[pos + 1];
             const double rhs = b[row], d = A.pinv[pos];
-            if (it.w >= 0) trs_gate(x + it.w, lane, abort_word);
             const double s = trs_gather_row(k0, k1, A.ci, A.v, x, lane, abort_word);
             if (lane == 0) st_l2(x + row, (rhs - s) * d);
         } else if (it.x == 2) {
@@ -1212,7 +1241,6 @@ __global__ void __launch_bounds__(kBlock)
             const int32_t pos = it.y;
             const int32_t k0 = A.crp[pos], k1 = A.crp[pos + 1];
             const double rhs = b[A.order[pos]];
-            if (it.w >= 0) trs_gate(x + it.w, lane, abort_word);
             const double s = trs_gather_row(k0, k1, A.cci, A.cv, x, lane, abort_word);
             if (lane == 0) st_l2(A.t + it.z, rhs - s);
         } else {
@@ -1226,9 +1254,8 @@ __global__ void __launch_bounds__(kBlock)
 #pragma unroll
             for (int jj = 0; jj < kTrsBlock / 32; ++jj) {
                 const int j = lane + 32 * jj;
-                dv[jj] = j <= r ? drow[j] : 0.0;
+                dv[jj] = j <= r ? __ldg(drow + j) : 0.0;
             }
-            trs_gate(tk + r, lane, abort_word);   // the row's own right-hand side
             double acc = 0.0;
 #pragma unroll
             for (int jj = 0; jj < kTrsBlock / 32; ++jj) {
@@ -1238,6 +1265,7 @@ __global__ void __launch_bounds__(kBlock)
             acc = warp_sum(acc);
             if (lane == 0) st_l2(x + row, acc);
         }
+        idx = __shfl_sync(0xffffffffu, next, 0);
     }
 }
 
