@@ -60,6 +60,7 @@ public:
     int32_t kind() const { return kind_; }
     int32_t size() const { return n_; }
     int64_t bytes_per_apply() const;
+    bool uses_level_graphs() const;   // ILU: the triangular solves are CUDA graphs of their own
     void release_host();   // drop the host copy below (large subdomains)
     PrecondData host;      // what was generated (parity tests read it through the C ABI)
 
@@ -200,6 +201,7 @@ private:
 
 public:
     int32_t num_items() const { return num_items_; }
+    bool uses_level_graph() const;      // which of the two solve() takes (see solvers.cu)
     int32_t error();                    // synchronises; non-zero: a wait timed out
 };
 

@@ -450,6 +450,11 @@ int64_t Preconditioner::bytes_per_apply() const
     return 0;
 }
 
+bool Preconditioner::uses_level_graphs() const
+{
+    return kind_ == PRECOND_ILU && Ltrs_ && (Ltrs_->uses_level_graph() || Utrs_->uses_level_graph());
+}
+
 void Preconditioner::apply(const double *r, double *z, double *dot_result, const int32_t *stop)
 {
     ctx_.use();

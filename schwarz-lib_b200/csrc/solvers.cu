@@ -112,8 +112,7 @@ void CgSolver::solve(const double *b, double *x, int32_t max_iters, double tol,
         force_while >= 0 ? (force_while != 0 || max_iters > kCgNoPoll) : true;
     // (the level-per-launch triangular solves of the ILU preconditioner are graphs of their
     // own and cannot be captured; the one-kernel solves can)
-    const char *trs_levels = std::getenv("SCHWZ_B200_TRS_LEVELS");
-    const bool ilu_levels = M_ && M_->kind() == PRECOND_ILU && trs_levels && trs_levels[0] == '1';
+    const bool ilu_levels = M_ && M_->kind() == PRECOND_ILU && M_->uses_level_graphs();
     const bool graphable = g_use_cg_graph && !not_graphable_ && !ilu_levels &&
                            (as_while || max_iters <= kCgNoPoll);
     if (graphable) {
@@ -1317,11 +1316,24 @@ int32_t TrsPlan::error()
     return e;
 }
 
+bool TrsPlan::uses_level_graph() const
+{
+    const char *e = std::getenv("SCHWZ_B200_TRS_LEVELS");
+    return e ? e[0] == '1' : num_launches() <= 4096;
+}
+
 void TrsPlan::solve(const double *b, double *x, const int32_t *stop)
 {
-    // SCHWZ_B200_TRS_LEVELS=1: the level-per-launch graph (A/B measurements)
-    const char *e = std::getenv("SCHWZ_B200_TRS_LEVELS");
-    if (e && e[0] == '1') solve_levels(b, x, stop);
+    // Which of the two wins is a matter of how deep the dependency chain is (measured,
+    // profiles/r2_sptrsv.md): the level-per-launch graph pays ~7 us per level but streams every
+    // level at full width with no polling; the one-kernel solve pays ~1.7 us per dependency hop
+    // (L2 round trips: the producer's store, the watcher's poll, the gather) plus a claim per
+    // item.  cfg5 factor (1 462 levels, 331 launches): 2.49 ms against 1.8 - 2.0 ms alone, but
+    // 0.37 against 0.74 ms with 8 solves side by side (polling warps of 8 kernels contend in
+    // L2).  ILU(0) wavefronts of a cfg2 strip (9 216 levels): 51 against 31 ms alone, 30 against
+    // 16.6 ms side by side.  So: the one-kernel solve for deep chains, the launch graph
+    // otherwise.  SCHWZ_B200_TRS_LEVELS=1 / 0 forces one or the other.
+    if (uses_level_graph()) solve_levels(b, x, stop);
     else solve_flow(b, x, stop);
 }
 
