@@ -24,6 +24,7 @@ void comm_allgather_f64(Comm &c, const double *dev_in, int count, double *dev_ou
 
 // one-CTA solvers for small subdomains (small_solvers.cu)
 extern bool g_use_cg_graph;        // SCHWZ_B200_NO_CG_GRAPH=1 turns the CG graph replay off
+extern bool g_trs_pdl;             // SCHWZ_B200_TRS_NO_PDL=1 turns programmatic dependent launch off
 extern bool g_gmres_cgs2;          // SCHWZ_B200_GMRES_MGS=1 turns CGS2 off in the one-CTA GMRES
 extern bool g_use_small_solvers;   // SCHWZ_B200_NO_SMALL=1 turns them off (A/B measurements)
 bool cg_small_fits(int64_t n);

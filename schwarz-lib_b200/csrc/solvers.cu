@@ -613,6 +613,7 @@ void GmresSolver::result(int32_t *iters, double *resnorm, double *resnorm0)
 // launch, not by bandwidth (tools/prof_trs.py).
 // Algorithmic bytes: 12*nnz + 20*rows.
 // =============================================================================
+bool g_trs_pdl = true;   // SCHWZ_B200_TRS_NO_PDL=1: plain stream order between the level kernels
 constexpr int kTrsWarps = kBlock / 32;
 constexpr int kTrsSmallLevel = 8 * kTrsWarps;   // levels of at most this many rows go into blocks
 
@@ -621,29 +622,69 @@ constexpr int kTrsSmallLevel = 8 * kTrsWarps;   // levels of at most this many r
 // two dependent loads (level bounds, order[i] -> rp[row]) out of the critical path of every
 // launch - these solves are bound by the memory latency of a short dependent chain per level,
 // not by bandwidth.
-__device__ __forceinline__ void trs_row(int32_t i, const int32_t *__restrict__ order,
+// Every kernel of a solve is launched with programmatic stream serialisation (PDL): it may
+// start while its predecessor is still running, does everything that does not depend on x
+// (level-order metadata, indices, values, right-hand side - the dependent chain of HBM loads
+// that made a level cost 7 us in round 1) and only then waits for the predecessor's results
+// with cudaGridDependencySynchronize().  b is stable during a solve: the first kernel of a
+// solve is launched without the attribute, i.e. behind a full dependency on whatever produced b.
+__device__ __forceinline__ void trs_row(int32_t i, int32_t e, int32_t stride,
+                                        const int32_t *__restrict__ order,
                                         const int32_t *__restrict__ prp,
                                         const int32_t *__restrict__ ci,
                                         const double *__restrict__ v,
                                         const double *__restrict__ pinv,
                                         const double *__restrict__ b, volatile double *x, int lane)
 {
-    const int32_t row = order[i];
-    const int32_t k1 = prp[i + 1];
-    const double rhs = b[row], d = pinv[i];   // independent of the gathers below
-    // 4 independent (index, value, x) gathers per lane in flight
-    double s = 0.0;
-    for (int32_t k = prp[i] + lane; k < k1; k += 128) {
-        double t[4] = {0.0, 0.0, 0.0, 0.0};
+    // prologue: the first row of this warp, up to its first round of entries
+    int32_t row = 0, k0 = 0, k1 = 0, c0[4] = {-1, -1, -1, -1};
+    double rhs = 0.0, d = 0.0, v0[4] = {0.0, 0.0, 0.0, 0.0};
+    if (i < e) {
+        row = order[i];
+        k0 = prp[i];
+        k1 = prp[i + 1];
+        rhs = b[row];
+        d = pinv[i];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-            const int32_t kk = k + 32 * u;
-            if (kk < k1) t[u] = v[kk] * x[ci[kk]];
+            const int32_t kk = k0 + lane + 32 * u;
+            if (kk < k1) {
+                c0[u] = ci[kk];
+                v0[u] = v[kk];
+            }
         }
-        s += (t[0] + t[1]) + (t[2] + t[3]);
     }
-    s = warp_sum(s);
-    if (lane == 0) x[row] = (rhs - s) * d;
+    cudaGridDependencySynchronize();
+    bool first = true;
+    for (; i < e; i += stride) {
+        if (!first) {
+            row = order[i];
+            k0 = prp[i];
+            k1 = prp[i + 1];
+            rhs = b[row];
+            d = pinv[i];
+        }
+        // 4 independent (index, value, x) gathers per lane in flight
+        double s = 0.0;
+        for (int32_t k = k0 + lane; k < k1; k += 128) {
+            double t[4] = {0.0, 0.0, 0.0, 0.0};
+            if (first && k == k0 + lane) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (c0[u] >= 0) t[u] = v0[u] * x[c0[u]];
+            } else {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int32_t kk = k + 32 * u;
+                    if (kk < k1) t[u] = v[kk] * x[ci[kk]];
+                }
+            }
+            s += (t[0] + t[1]) + (t[2] + t[3]);
+        }
+        s = warp_sum(s);
+        if (lane == 0) x[row] = (rhs - s) * d;
+        first = false;
+    }
 }
 
 // one launch = positions [a, e) of the level order (one level), a warp per row
@@ -653,11 +694,17 @@ __global__ void __launch_bounds__(kBlock)
                       const double *__restrict__ v, const double *__restrict__ pinv,
                       const double *__restrict__ b, double *x, const int32_t *stop)
 {
-    if (stop != nullptr && *stop != 0) return;
+    // let the next kernel of the solve start its own prologue right away: it still waits for
+    // the whole of this grid in its cudaGridDependencySynchronize()
+    cudaTriggerProgrammaticLaunchCompletion();
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * kBlock + threadIdx.x) >> 5;
     const int nwarps = (gridDim.x * kBlock) >> 5;
-    for (int32_t i = a + warp; i < e; i += nwarps) trs_row(i, order, prp, ci, v, pinv, b, x, lane);
+    if (stop != nullptr && *stop != 0) {   // (the flag is set outside the solve)
+        cudaGridDependencySynchronize();
+        return;
+    }
+    trs_row(a + warp, e, nwarps, order, prp, ci, v, pinv, b, x, lane);
 }
 
 // A wide level of SHORT rows (the leaves of a nested-dissection factor: 10^5 rows of 0..8
@@ -669,19 +716,40 @@ __global__ void __launch_bounds__(kBlock)
                             const double *__restrict__ v, const double *__restrict__ pinv,
                             const double *__restrict__ b, double *x, const int32_t *stop)
 {
-    if (stop != nullptr && *stop != 0) return;
-    for (int32_t i = a + blockIdx.x * kBlock + threadIdx.x; i < e; i += gridDim.x * kBlock) {
-        const int32_t row = order[i];
+    cudaTriggerProgrammaticLaunchCompletion();
+    const bool off = stop != nullptr && *stop != 0;
+    int32_t i = a + blockIdx.x * kBlock + threadIdx.x;
+    int32_t row = 0, k0 = 0, k1 = 0;
+    double rhs = 0.0, d = 0.0;
+    if (!off && i < e) {
+        row = order[i];
+        k0 = prp[i];
+        k1 = prp[i + 1];
+        rhs = b[row];
+        d = pinv[i];
+    }
+    cudaGridDependencySynchronize();
+    if (off) return;
+    bool first = true;
+    for (; i < e; i += gridDim.x * kBlock) {
+        if (!first) {
+            row = order[i];
+            k0 = prp[i];
+            k1 = prp[i + 1];
+            rhs = b[row];
+            d = pinv[i];
+        }
         double s = 0.0;
-        for (int32_t k = prp[i]; k < prp[i + 1]; ++k) s += v[k] * x[ci[k]];
-        x[row] = (b[row] - s) * pinv[i];
+        for (int32_t k = k0; k < k1; ++k) s += v[k] * x[ci[k]];
+        x[row] = (rhs - s) * d;
+        first = false;
     }
 }
 
 // One block of a small-level run: warps form t_i = b_i - sum over the entries OUTSIDE the
-// block (all of them already solved by earlier launches); the last CTA to finish multiplies
-// by the block's explicit inverse: x_K = Dinv_K t.
-constexpr int kTrsBlock = 128;
+// block (all of them already solved by earlier launches); a second launch multiplies by the
+// block's explicit inverse: x_K = Dinv_K t.
+constexpr int kTrsBlock = 512;
 
 // phase A: t_i = b_i - (entries of row i outside the block) . x
 __global__ void __launch_bounds__(kBlock)
@@ -691,20 +759,40 @@ __global__ void __launch_bounds__(kBlock)
                        const double *__restrict__ x, double *__restrict__ t_scratch,
                        const int32_t *stop, int cta_per_row)
 {
-    if (stop != nullptr && *stop != 0) return;
+    cudaTriggerProgrammaticLaunchCompletion();
+    const bool off = stop != nullptr && *stop != 0;
     const int lane = threadIdx.x & 31;
     if (cta_per_row) {
         // long rows (the dense separator triangles: hundreds to thousands of outside entries
         // per row): the whole CTA strides over one row, 4 independent gathers per thread in
-        // flight; with a warp per row only 128 warps would carry the block's 1-2 MB
+        // flight; with a warp per row only a few warps would carry the block's megabytes
         __shared__ double s_red[kBlock / 32];
+        int32_t k0 = 0, k1 = 0, c0 = -1;
+        double rhs = 0.0, v0 = 0.0;
+        if (!off && (int32_t)blockIdx.x < nrows) {
+            const int32_t p = pos0 + blockIdx.x;
+            k0 = crp[p];
+            k1 = crp[p + 1];
+            rhs = b[order[p]];
+            if (k0 + (int32_t)threadIdx.x < k1) {
+                c0 = cci[k0 + threadIdx.x];
+                v0 = cv[k0 + threadIdx.x];
+            }
+        }
+        cudaGridDependencySynchronize();
+        if (off) return;
+        bool first = true;
         for (int32_t i = blockIdx.x; i < nrows; i += gridDim.x) {
-            const int32_t p = pos0 + i;
-            const int32_t k0 = crp[p], k1 = crp[p + 1];
-            const double rhs = b[order[p]];
+            if (!first) {
+                const int32_t p = pos0 + i;
+                k0 = crp[p];
+                k1 = crp[p + 1];
+                rhs = b[order[p]];
+            }
             double s = 0.0;
             for (int32_t k = k0 + threadIdx.x; k < k1; k += 4 * kBlock) {
-                double t0 = cv[k] * x[cci[k]], t1 = 0.0, t2 = 0.0, t3 = 0.0;
+                double t0 = (first && k == k0 + (int32_t)threadIdx.x) ? v0 * x[c0] : cv[k] * x[cci[k]];
+                double t1 = 0.0, t2 = 0.0, t3 = 0.0;
                 if (k + kBlock < k1) t1 = cv[k + kBlock] * x[cci[k + kBlock]];
                 if (k + 2 * kBlock < k1) t2 = cv[k + 2 * kBlock] * x[cci[k + 2 * kBlock]];
                 if (k + 3 * kBlock < k1) t3 = cv[k + 3 * kBlock] * x[cci[k + 3 * kBlock]];
@@ -712,41 +800,77 @@ __global__ void __launch_bounds__(kBlock)
             }
             s = block_sum(s, s_red);
             if (threadIdx.x == 0) t_scratch[i] = rhs - s;
+            first = false;
         }
         return;
     }
     const int warp = (blockIdx.x * kBlock + threadIdx.x) >> 5;
     const int nwarps = (gridDim.x * kBlock) >> 5;
+    int32_t k0 = 0, k1 = 0, c0 = -1;
+    double rhs = 0.0, v0 = 0.0;
+    if (!off && warp < nrows) {
+        const int32_t p = pos0 + warp;
+        k0 = crp[p];
+        k1 = crp[p + 1];
+        rhs = b[order[p]];
+        if (k0 + lane < k1) {
+            c0 = cci[k0 + lane];
+            v0 = cv[k0 + lane];
+        }
+    }
+    cudaGridDependencySynchronize();
+    if (off) return;
+    bool first = true;
     for (int32_t i = warp; i < nrows; i += nwarps) {
-        const int32_t p = pos0 + i;
-        const double rhs = b[order[p]];
+        if (!first) {
+            const int32_t p = pos0 + i;
+            k0 = crp[p];
+            k1 = crp[p + 1];
+            rhs = b[order[p]];
+        }
         double s = 0.0;
-        for (int32_t k = crp[p] + lane; k < crp[p + 1]; k += 32) s += cv[k] * x[cci[k]];
+        for (int32_t k = k0 + lane; k < k1; k += 32)
+            s += (first && k == k0 + lane) ? v0 * x[c0] : cv[k] * x[cci[k]];
         s = warp_sum(s);
         if (lane == 0) t_scratch[i] = rhs - s;
+        first = false;
     }
 }
 
 // phase B, its own launch (the kernel boundary replaces a fence + ticket + reload in the last
 // CTA): x_K = Dinv t.  Dinv row-major (lower triangle); a warp per row with the lanes across
-// the columns (coalesced), four rows of a warp in flight at once; 4 CTAs cover 128 rows.
+// the columns (coalesced), four rows of a warp in flight at once.  Before it waits for phase A
+// the kernel pulls its rows of Dinv towards L2.
 __global__ void __launch_bounds__(kBlock)
     trs_block_b_kernel(int32_t pos0, int32_t nrows, const int32_t *__restrict__ order,
                        const double *__restrict__ dinv, const double *__restrict__ t_scratch,
                        double *__restrict__ x, const int32_t *stop)
 {
     __shared__ double s_t[kTrsBlock];
-    if (stop != nullptr && *stop != 0) return;
+    cudaTriggerProgrammaticLaunchCompletion();
+    const bool off = stop != nullptr && *stop != 0;
     const int lane = threadIdx.x & 31;
-    for (int i = threadIdx.x; i < nrows; i += kBlock) s_t[i] = t_scratch[i];
-    __syncthreads();
     const int w = blockIdx.x * (kBlock / 32) + (threadIdx.x >> 5);
     const int r0 = 4 * w;
+    if (!off && r0 < nrows) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int r = r0 + u;
+            if (r < nrows)
+                for (int j = 16 * lane; j <= r; j += 16 * 32)   // one 128-byte line per lane
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(dinv + (size_t)r * nrows + j));
+        }
+    }
+    cudaGridDependencySynchronize();
+    if (off) return;
+    for (int i = threadIdx.x; i < nrows; i += kBlock) s_t[i] = t_scratch[i];
+    __syncthreads();
     if (r0 >= nrows) return;
     double acc[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll
+#pragma unroll 4
     for (int jj = 0; jj < kTrsBlock / 32; ++jj) {
         const int j = lane + 32 * jj;
+        if (j > r0 + 3) break;
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const int r = r0 + u;
@@ -810,7 +934,7 @@ TrsPlan::TrsPlan(const Ctx &ctx, int32_t n, const int32_t *rp, const int32_t *ci
     order_ = ctx.upload(order.data(), (size_t)n);
 
     // ---- segments: wide levels one by one, runs of small levels cut into blocks ----------
-    static_assert(kTrsBlock % 32 == 0 && kTrsBlock <= kBlock, "trs_block_kernel stages t in one pass");
+    static_assert(kTrsBlock % 32 == 0, "the inverse blocks are walked 32 columns at a time");
     std::vector<int32_t> crp(1, 0), cci, pos_in_block((size_t)n, -1);
     std::vector<double> cv, dinv;
     std::vector<int32_t> chain_first;   // position of every chain row -> index into crp
@@ -1022,28 +1146,44 @@ void TrsPlan::solve_levels(const double *b, double *x, const int32_t *stop)
     }
     cudaGraph_t graph = nullptr;
     SCHWZ_CUDA(cudaStreamBeginCapture(ctx_.stream, cudaStreamCaptureModeThreadLocal));
+    // every launch but the first may overlap its predecessor's tail (see trs_row)
+    bool first_launch = true;
+    auto launch = [&](auto kernel, int grid, auto... args) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)grid);
+        cfg.blockDim = dim3(kBlock);
+        cfg.stream = ctx_.stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = (first_launch || !g_trs_pdl) ? 0 : 1;
+        first_launch = false;
+        SCHWZ_CUDA(cudaLaunchKernelEx(&cfg, kernel, args...));
+    };
     for (const Segment &sg : segments_) {
         if (sg.kind == 0) {
             const int32_t l = sg.a;
             const int32_t rows = level_ptr_[l + 1] - level_ptr_[l];
             if (sg.mode == 1) {
                 const int grid = std::min((rows + kBlock - 1) / kBlock, ctx_.vec_grid());
-                trs_level_thread_kernel<<<grid, kBlock, 0, ctx_.stream>>>(
-                    level_ptr_[l], level_ptr_[l + 1], order_, rp_, ci_, v_, inv_diag_, b, x, stop);
+                launch(trs_level_thread_kernel, grid, level_ptr_[l], level_ptr_[l + 1],
+                       (const int32_t *)order_, (const int32_t *)rp_, (const int32_t *)ci_,
+                       (const double *)v_, (const double *)inv_diag_, b, x, stop);
                 continue;
             }
             const int grid = std::min((rows + kTrsWarps - 1) / kTrsWarps, ctx_.vec_grid());
-            trs_levels_kernel<<<grid, kBlock, 0, ctx_.stream>>>(level_ptr_[l], level_ptr_[l + 1],
-                                                                order_, rp_, ci_, v_, inv_diag_,
-                                                                b, x, stop);
+            launch(trs_levels_kernel, grid, level_ptr_[l], level_ptr_[l + 1],
+                   (const int32_t *)order_, (const int32_t *)rp_, (const int32_t *)ci_,
+                   (const double *)v_, (const double *)inv_diag_, b, x, stop);
         } else {
             const int grid = sg.mode == 2 ? sg.b : std::max(1, (sg.b + kTrsWarps - 1) / kTrsWarps);
-            trs_block_a_kernel<<<grid, kBlock, 0, ctx_.stream>>>(
-                sg.a, sg.b, order_, chain_rp_, chain_ci_, chain_v_, b, x, block_t_, stop,
-                sg.mode == 2 ? 1 : 0);
-            trs_block_b_kernel<<<(sg.b + 4 * kTrsWarps - 1) / (4 * kTrsWarps), kBlock, 0,
-                                 ctx_.stream>>>(sg.a, sg.b, order_, dinv_ + sg.dinv_off, block_t_,
-                                                x, stop);
+            launch(trs_block_a_kernel, grid, sg.a, sg.b, (const int32_t *)order_,
+                   (const int32_t *)chain_rp_, (const int32_t *)chain_ci_, (const double *)chain_v_,
+                   b, (const double *)x, block_t_, stop, sg.mode == 2 ? 1 : 0);
+            launch(trs_block_b_kernel, (sg.b + 4 * kTrsWarps - 1) / (4 * kTrsWarps), sg.a, sg.b,
+                   (const int32_t *)order_, (const double *)(dinv_ + sg.dinv_off),
+                   (const double *)block_t_, x, stop);
         }
     }
     SCHWZ_CUDA(cudaStreamEndCapture(ctx_.stream, &graph));
