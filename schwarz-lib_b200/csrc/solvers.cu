@@ -1456,23 +1456,26 @@ int32_t TrsPlan::error()
     return e;
 }
 
+// The level-per-launch graph (with programmatic dependent launch) is the default; the one-kernel
+// solve stays selectable with SCHWZ_B200_TRS_LEVELS=0 (measurements: profiles/r2_sptrsv.md).
 bool TrsPlan::uses_level_graph() const
 {
     const char *e = std::getenv("SCHWZ_B200_TRS_LEVELS");
-    return e ? e[0] == '1' : num_launches() <= 4096;
+    return e ? e[0] != '0' : true;
 }
 
 void TrsPlan::solve(const double *b, double *x, const int32_t *stop)
 {
-    // Which of the two wins is a matter of how deep the dependency chain is (measured,
-    // profiles/r2_sptrsv.md): the level-per-launch graph pays ~7 us per level but streams every
-    // level at full width with no polling; the one-kernel solve pays ~1.7 us per dependency hop
-    // (L2 round trips: the producer's store, the watcher's poll, the gather) plus a claim per
-    // item.  cfg5 factor (1 462 levels, 331 launches): 2.49 ms against 1.8 - 2.0 ms alone, but
-    // 0.37 against 0.74 ms with 8 solves side by side (polling warps of 8 kernels contend in
-    // L2).  ILU(0) wavefronts of a cfg2 strip (9 216 levels): 51 against 31 ms alone, 30 against
-    // 16.6 ms side by side.  So: the one-kernel solve for deep chains, the launch graph
-    // otherwise.  SCHWZ_B200_TRS_LEVELS=1 / 0 forces one or the other.
+    // Measured (profiles/r2_sptrsv.md), L + U pair of the cfg5 factor (1 462 levels) alone / 8
+    // side by side, and of the ILU(0) wavefronts of a cfg2 strip (9 216 levels) alone / 2 side
+    // by side:
+    //   round 1 level graph (128-row blocks)          2489 / 372 us      51.0 / 30.0 ms
+    //   one-kernel solve (trs_flow_kernel)             1811 / 740 us      30.9 / 16.6 ms
+    //   level graph, 512-row blocks                    1850 / 325 us
+    //   level graph, 512-row blocks + PDL prologues    1267 / 256 us      30.6 / 15.7 ms
+    // The one-kernel solve removes the launch chain but pays ~1.7 us per dependency hop (several
+    // L2 round trips) and its polling warps contend when solves share the GPU; the launch graph
+    // with dependency-free prologues is as fast on deep chains and faster everywhere else.
     if (uses_level_graph()) solve_levels(b, x, stop);
     else solve_flow(b, x, stop);
 }
