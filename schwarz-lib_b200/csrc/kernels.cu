@@ -70,7 +70,7 @@ DeviceCsr *csr_upload(const Ctx &ctx, int32_t nrows, int32_t ncols, const int32_
     A->nnz = nrows > 0 ? rp[nrows] : 0;
     // Row tiling: greedy, <= kBlock rows and <= kSpmvTile nnz per CTA; a row
     // longer than the tile gets a CTA of its own (long-row path).
-    const int rpt = (g_spmv_variant >= 3) ? 2 : 1;
+    const int rpt = (g_spmv_variant >= 3 && g_spmv_variant < 10) ? 2 : 1;
     A->rows_per_tile = kBlock * rpt;
     const int32_t tile_rows = A->rows_per_tile, tile_nnz = kSpmvTile * rpt;
     std::vector<int32_t> blk;
@@ -526,6 +526,9 @@ static void launch_spmv_tma(const Ctx &ctx, const DeviceCsr &A, double alpha, co
         switch (g_spmv_variant) {
         case 0: SCHWZ_TMA(1, 3, 2); break;
         case 2: SCHWZ_TMA(1, 4, 2); break;
+        case 10: SCHWZ_TMA(1, 3, 3); break;
+        case 11: SCHWZ_TMA(1, 2, 5); break;
+        case 12: SCHWZ_TMA(1, 2, 3); break;
         default: SCHWZ_TMA(1, 2, 4); break;   // measured best: 0.946 of HBM peak (profiles/)
         }
     } else {

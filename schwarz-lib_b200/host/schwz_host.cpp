@@ -231,11 +231,18 @@ void Initialize<V, I>::setup_vectors(const Settings &settings, const Metadata<V,
 // Communicate
 // =============================================================================
 template <typename V, typename I, typename M>
-void Communicate<V, I, M>::local_to_global_vector(const Settings &, const Metadata<V, I> &,
+void Communicate<V, I, M>::local_to_global_vector(const Settings &settings, const Metadata<V, I> &,
                                                   const std::shared_ptr<gko::matrix::Dense<V>> &,
                                                   std::shared_ptr<gko::matrix::Dense<V>> &)
 {
-    // source/communicate.cpp:65-94 (solution_based): x[own] <- local_solution
+    // source/communicate.cpp:65-94.  Only the solution_based update exists here.  The
+    // residual_based branch (:86-90) is unreachable from bench_ras and cannot run upstream
+    // either (it add_scales a local_size_x vector with a local_size one); selecting it is an
+    // error rather than a silent fall-back to solution_based.
+    if (settings.convergence_settings.convergence_crit ==
+        Settings::convergence_settings::local_convergence_crit::residual_based)
+        throw std::runtime_error("convergence_settings.convergence_crit = residual_based is not "
+                                 "implemented (source/communicate.cpp:86-90); use solution_based");
     B200_CHECK(schwz_b200_ras_restrict(comm_dev_->ras));
 }
 

@@ -40,6 +40,16 @@ CASES = {
     "cfg3_ani4_metis_P8_gmres": dict(P=8, matrix="ani4_crop", partition="metis", max_iters=800,
                                      tolerance=1e-6, non_symmetric=True, restart_iter=30,
                                      snap=[1, 3, 10]),
+    # the other shipped matrix, matrices/ani3_crop.mtx (N = 741)
+    "cfg3_ani3_metis_P2_gmres": dict(P=2, matrix="ani3_crop", partition="metis", max_iters=800,
+                                     tolerance=1e-6, non_symmetric=True, restart_iter=30,
+                                     snap=[1, 3, 10]),
+    "cfg3_ani3_metis_P4_gmres": dict(P=4, matrix="ani3_crop", partition="metis", max_iters=800,
+                                     tolerance=1e-6, non_symmetric=True, restart_iter=30,
+                                     snap=[1, 3, 10]),
+    "cfg3_ani3_metis_P8_gmres": dict(P=8, matrix="ani3_crop", partition="metis", max_iters=800,
+                                     tolerance=1e-6, non_symmetric=True, restart_iter=30,
+                                     snap=[1, 3, 10]),
 }
 
 
@@ -99,9 +109,11 @@ def main_sampled():
         print(name, "iters", out["iters"].tolist(), os.path.getsize(path), "bytes")
 
 
-def main():
+def main(only=None):
     import ref as R
     for name, c in CASES.items():
+        if only and only not in name:
+            continue
         c = dict(c)
         P = c.pop("P")
         snap = c.pop("snap")
@@ -141,6 +153,8 @@ def main():
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "sampled":
         main_sampled()
+    elif len(sys.argv) > 1:
+        main(only=sys.argv[1])     # e.g. "ani3": only the cases whose name contains it
     else:
         main()
         main_sampled()

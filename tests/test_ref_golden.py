@@ -37,7 +37,20 @@ CONFIG = {
                                      kw=dict(non_symmetric=True, restart_iter=30)),
     "cfg3_ani4_metis_P8_gmres": dict(P=8, matrix="ani4", partition="metis", tol=1e-6, max_iters=800,
                                      kw=dict(non_symmetric=True, restart_iter=30)),
+    "cfg3_ani3_metis_P2_gmres": dict(P=2, matrix="ani3", partition="metis", tol=1e-6, max_iters=800,
+                                     kw=dict(non_symmetric=True, restart_iter=30)),
+    "cfg3_ani3_metis_P4_gmres": dict(P=4, matrix="ani3", partition="metis", tol=1e-6, max_iters=800,
+                                     kw=dict(non_symmetric=True, restart_iter=30)),
+    "cfg3_ani3_metis_P8_gmres": dict(P=8, matrix="ani3", partition="metis", tol=1e-6, max_iters=800,
+                                     kw=dict(non_symmetric=True, restart_iter=30)),
 }
+
+
+def _ani(name, ani4):
+    if name == "ani4":
+        return ani4
+    z = np.load(os.path.join(GOLDEN, "%s_crop.npz" % name))
+    return z["rowptr"], z["col"], z["val"]
 
 
 def _setup(sz, ani4, case):
@@ -45,6 +58,7 @@ def _setup(sz, ani4, case):
     g = np.load(os.path.join(GOLDEN, "ref_%s.npz" % case))
     P = c["P"]
     if "matrix" in c:
+        ani4 = _ani(c["matrix"], ani4)
         mat, N = ani4, len(ani4[0]) - 1
     else:
         mat, N = ("laplacian2d", c["n"]), c["n"] ** 2

@@ -175,6 +175,27 @@ def test_cfg3_ani4_metis_gmres(ref, orc, sz, ani4, tmp_path, P):
     same_history(rr, ob, P)
 
 
+@pytest.mark.parametrize("P", [2, 4, 8])
+def test_cfg3_ani3_metis_gmres(ref, orc, sz, tmp_path, P):
+    """the other shipped matrix, matrices/ani3_crop.mtx: same configuration"""
+    import os
+    from conftest import GOLDEN
+    z = np.load(os.path.join(GOLDEN, "ani3_crop.npz"))
+    ani3 = (z["rowptr"], z["col"], z["val"])
+    orc.set_threads(1)
+    path = write_mtx(tmp_path / "ani3.mtx", ani3)
+    rr = ref.Run(P, matrix_file=path, partition="metis", overlap=2, max_iters=60,
+                 tolerance=1e-6, local_tol=1e-12, non_symmetric=True, restart_iter=30,
+                 enable_global_check=True, record_iterates=True)
+    part = sz.partition_metis(ani3[0], ani3[1], P)
+    assert np.array_equal(rr.vec("partition_indices", 0), part)
+    ob = orc.Problem(*ani3, P, part=part)
+    ob.configure(tolerance=1e-6, local_tol=1e-12, max_iters=60, non_symmetric=True,
+                 restart_iter=30, enable_global_check=True)
+    same_setup(rr, ob, P, True)
+    same_history(rr, ob, P)
+
+
 def test_ani4_regular_cg_fixed_budget(ref, orc, ani4, tmp_path):
     """fixed local budget (local_max_iters) instead of a converged local solve."""
     orc.set_threads(1)
