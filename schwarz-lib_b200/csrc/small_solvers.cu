@@ -137,16 +137,21 @@ __global__ void __launch_bounds__(kSmallThreads, 1)
 bool cg_small_fits(int64_t n) { return n > 0 && (4 * n + kSmallBuf) * 8 <= 220 * 1024; }
 
 // threads by size: few warps make the barriers cheap, many warps hide the gathers
-static int small_threads(int64_t n)
+static int small_threads(int64_t n, bool few_barriers = false)
 {
     static int forced = -1;
     if (forced < 0) {
-        const char *e = std::getenv("SCHWZ_B200_SMALL_THREADS");   // A/B aid: 128, 256 or 1024
+        const char *e = std::getenv("SCHWZ_B200_SMALL_THREADS");   // A/B aid: 128, 256, 512 or 1024
         forced = e ? std::atoi(e) : 0;
     }
-    if (forced == 128 || forced == 256 || forced == 1024) return forced;
-    // measured (tools/prof_small.py): 457 rows 10.8 / 14.5 / 14.5 us per GMRES(30) step with
-    // 256 / 128 / 1024 threads; from 827 rows up 1024 threads win (18.1 vs 18.3 vs 19.8 us)
+    if (forced == 128 || forced == 256 || forced == 512 || forced == 1024) return forced;
+    // measured (tools/prof_small.py, profiles/r2_cfg3.md): with one CTA-wide reduction per
+    // Gram-Schmidt projection (MGS, and CG) 457 rows take 10.8 / 14.5 / 14.5 us per GMRES(30)
+    // step with 256 / 128 / 1024 threads; from 827 rows up 1024 threads win.  With CGS2 (three
+    // barriers per step) the kernel is bound by the instructions each warp has to issue, and
+    // more warps pay: cfg3 at P = 8 (457 rows) 377 / 456 / 442 outer iterations per second
+    // with 256 / 512 / 1024 threads, P = 2 (1600 rows) 92 / 121 / 131.
+    if (few_barriers) return n <= 640 ? 512 : 1024;
     return n <= 640 ? 256 : 1024;
 }
 
@@ -157,14 +162,15 @@ void launch_cg_small(const Ctx &ctx, const DeviceCsr &A, const double *b, double
     const size_t smem = (4 * (size_t)A.nrows + kSmallBuf) * sizeof(double);
     static std::atomic<bool> configured[64];
     if (!configured[ctx.device].load(std::memory_order_acquire)) {
-        for (auto *k : {cg_small_kernel<128>, cg_small_kernel<256>, cg_small_kernel<1024>})
+        for (auto *k : {cg_small_kernel<128>, cg_small_kernel<256>, cg_small_kernel<512>,
+                        cg_small_kernel<1024>})
             SCHWZ_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             220 * 1024));
         configured[ctx.device].store(true, std::memory_order_release);
     }
     const int th = small_threads(A.nrows);
     auto *k = th == 128 ? cg_small_kernel<128> : th == 256 ? cg_small_kernel<256>
-                                                           : cg_small_kernel<1024>;
+              : th == 512 ? cg_small_kernel<512> : cg_small_kernel<1024>;
     k<<<1, th, smem, ctx.stream>>>(A.nrows, A.rp, A.ci, A.v, b, x, max_iters, tol, out, outer_stop);
     SCHWZ_CUDA(cudaGetLastError());
     count_launch();
@@ -434,16 +440,17 @@ void launch_gmres_small(const Ctx &ctx, const DeviceCsr &A, const double *b, dou
     ctx.use();
     static std::atomic<bool> configured[64];
     if (!configured[ctx.device].load(std::memory_order_acquire)) {
-        for (auto *k : {gmres_small_kernel<128>, gmres_small_kernel<256>, gmres_small_kernel<1024>})
+        for (auto *k : {gmres_small_kernel<128>, gmres_small_kernel<256>, gmres_small_kernel<512>,
+                        gmres_small_kernel<1024>})
             SCHWZ_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             220 * 1024));
         configured[ctx.device].store(true, std::memory_order_release);
     }
     const bool basis = gmres_small_smem(A.nrows, m, true) <= 220 * 1024;
     const bool matrix = gmres_small_smem(A.nrows, m, basis, A.nnz) <= 220 * 1024;
-    const int th = small_threads(A.nrows);
+    const int th = small_threads(A.nrows, g_gmres_cgs2);
     auto *k = th == 128 ? gmres_small_kernel<128> : th == 256 ? gmres_small_kernel<256>
-                                                              : gmres_small_kernel<1024>;
+              : th == 512 ? gmres_small_kernel<512> : gmres_small_kernel<1024>;
     k<<<1, th, gmres_small_smem(A.nrows, m, basis, matrix ? A.nnz : -1), ctx.stream>>>(
         A.nrows, A.rp, A.ci, A.v, b, x, V, m, max_iters, tol, resnorm_out, r0_out, total_out,
         basis ? 1 : 0, matrix ? 1 : 0, outer_stop, g_gmres_cgs2 ? 1 : 0);
