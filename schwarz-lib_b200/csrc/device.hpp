@@ -74,10 +74,11 @@ struct DeviceCsr {
     int32_t *blk_row = nullptr;
     bool has_long_row = false;
     int32_t rows_per_tile = kBlock;
-    // Compact column stream of the pipelined SpMV: when the columns of every row tile span
-    // less than 2^16 (stencil / banded local matrices: a 256-row tile of a cfg2 strip spans
-    // 16 640 columns) the kernel reads 16-bit offsets from the tile's first column instead of
-    // 32-bit indices: 10 instead of 12 B per non-zero from HBM.  ci stays for everybody else.
+    // Compact column stream of the pipelined SpMV: a row tile whose columns span less than
+    // 2^16 (stencil / banded local matrices: a 256-row tile of a cfg2 strip spans 16 640
+    // columns) is read as 16-bit offsets from the tile's first column instead of 32-bit
+    // indices: 10 instead of 12 B per non-zero from HBM.  Other tiles (tile_col0 < 0: the
+    // overlap rows of a strip couple to both ends of the own block) keep their 32-bit indices.
     uint16_t *ci16 = nullptr;
     int32_t *tile_col0 = nullptr;
     ~DeviceCsr();

@@ -117,9 +117,13 @@ DeviceCsr *csr_upload(const Ctx &ctx, int32_t nrows, int32_t ncols, const int32_
     A->v = upload_padded(v, (size_t)A->nnz, double(0));
     A->blk_row = ctx.upload(blk.data(), blk.size());
     if (g_spmv_col16 && !A->has_long_row && A->nnz > 0) {
+        // per tile: first column and whether the tile's columns fit 16 bits from there.  Tiles
+        // that do not (the overlap rows of a strip couple to both ends of the own block) keep
+        // their 32-bit indices: tile_col0 = -1.
         std::vector<int32_t> col0((size_t)A->nblocks, 0);
-        bool fits = true;
-        for (int32_t b = 0; b < A->nblocks && fits; ++b) {
+        std::vector<uint16_t> c16((size_t)A->nnz, 0);
+        int64_t narrow_nnz = 0;
+        for (int32_t b = 0; b < A->nblocks; ++b) {
             const int32_t k0 = rp[blk[b]], k1 = rp[blk[b + 1]];
             if (k0 == k1) continue;
             int32_t lo = ci[k0], hi = ci[k0];
@@ -127,14 +131,15 @@ DeviceCsr *csr_upload(const Ctx &ctx, int32_t nrows, int32_t ncols, const int32_
                 lo = std::min(lo, ci[k]);
                 hi = std::max(hi, ci[k]);
             }
-            col0[b] = lo;
-            fits = (int64_t)hi - lo < 65536;
+            if ((int64_t)hi - lo < 65536) {
+                col0[b] = lo;
+                for (int32_t k = k0; k < k1; ++k) c16[k] = (uint16_t)(ci[k] - lo);
+                narrow_nnz += k1 - k0;
+            } else {
+                col0[b] = -1;
+            }
         }
-        if (fits) {
-            std::vector<uint16_t> c16((size_t)A->nnz);
-            for (int32_t b = 0; b < A->nblocks; ++b)
-                for (int32_t k = rp[blk[b]]; k < rp[blk[b + 1]]; ++k)
-                    c16[k] = (uint16_t)(ci[k] - col0[b]);
+        if (narrow_nnz * 10 >= A->nnz * 9) {   // worth it when (almost) every tile is narrow
             // 16-byte granules of 8 entries: pad by 16
             uint16_t *d = ctx.alloc_zero<uint16_t>((size_t)A->nnz + 16);
             SCHWZ_CUDA(cudaMemcpyAsync(d, c16.data(), c16.size() * sizeof(uint16_t),
@@ -259,7 +264,7 @@ constexpr int kSpmvThreads = kBlock + 32;   // 8 consumer warps + 1 producer war
 template <int RPT, typename ColT>
 struct __align__(16) SpmvStage {
     double val[kSpmvTile * RPT + 16];
-    ColT col[kSpmvTile * RPT + 16];
+    int32_t col[kSpmvTile * RPT + 16];   // 32-bit indices, or 16-bit offsets in its first half
     int32_t rp[kBlock * RPT + 8];
 };
 template <int RPT, int STAGES, typename ColT>
@@ -317,12 +322,13 @@ __device__ __forceinline__ void consumer_sync()
     asm volatile("bar.sync 1, %0;" ::"n"(kBlock) : "memory");
 }
 
-// ColT = int32_t: column indices as stored; uint16_t: offsets from tile_col0[tile]
+// ColT = int32_t: column indices as stored; uint16_t: per tile either 16-bit offsets from
+// tile_col0[tile] (ci16) or, where tile_col0[tile] < 0, the 32-bit indices (ci)
 template <int EPI, int RPT, int STAGES, int CTAS, typename ColT>
 __global__ void __launch_bounds__(kSpmvThreads, CTAS)
     csr_spmv_tma_kernel(int32_t ntiles, const int32_t *__restrict__ blk_row,
-                        const int32_t *__restrict__ rp, const ColT *__restrict__ ci,
-                        const int32_t *__restrict__ tile_col0,
+                        const int32_t *__restrict__ rp, const int32_t *__restrict__ ci,
+                        const uint16_t *__restrict__ ci16, const int32_t *__restrict__ tile_col0,
                         const double *__restrict__ v, const double *__restrict__ x, double alpha,
                         double beta, const double *y_in, double *y_out, const double *dot_with,
                         double *partials, unsigned int *ticket, double *result, int32_t red_rows,
@@ -332,7 +338,7 @@ __global__ void __launch_bounds__(kSpmvThreads, CTAS)
     using Smem = SpmvSmem<RPT, STAGES, ColT>;
     Smem &S = *reinterpret_cast<Smem *>(smem_raw);
     if (stop != nullptr && *stop != 0) return;
-    constexpr int32_t G = 16 / (int)sizeof(ColT);   // entries per 16-byte granule of the col stream
+    constexpr bool kCol16 = sizeof(ColT) == 2;
 
     const int t = threadIdx.x;
     if (t == 0) {
@@ -354,15 +360,19 @@ __global__ void __launch_bounds__(kSpmvThreads, CTAS)
                 const int s = it % STAGES;
                 const int32_t r0 = blk_row[b], r1 = blk_row[b + 1];
                 const int32_t k0 = rp[r0], k1 = rp[r1];
-                const int32_t k0a = k0 & ~(G - 1), k1a = (k1 + G - 1) & ~(G - 1);   // granules
+                // 16-byte granules of the column stream: 8 entries of 16 bits, 4 of 32
+                const bool narrow = kCol16 && tile_col0[b] >= 0;
+                const int32_t G = narrow ? 8 : 4;
+                const uint32_t cb = narrow ? 2u : 4u;
+                const int32_t k0a = k0 & ~(G - 1), k1a = (k1 + G - 1) & ~(G - 1);
                 const int32_t r0a = r0 & ~3, r1a = (r1 + 1 + 3) & ~3;
                 const uint32_t nv = (uint32_t)(k1a - k0a), nr = (uint32_t)(r1a - r0a);
                 mbar_wait(&S.empty[s], ((it / STAGES) & 1) ^ 1);
-                mbar_expect_tx(&S.full[s], nv * (8u + (uint32_t)sizeof(ColT)) + nr * 4u);
+                mbar_expect_tx(&S.full[s], nv * (8u + cb) + nr * 4u);
                 if (nv) {
                     bulk_g2s(S.st[s].val, v + k0a, nv * 8u, &S.full[s], policy);
-                    bulk_g2s(S.st[s].col, ci + k0a, nv * (uint32_t)sizeof(ColT), &S.full[s],
-                             policy);
+                    if (narrow) bulk_g2s(S.st[s].col, ci16 + k0a, nv * 2u, &S.full[s], policy);
+                    else bulk_g2s(S.st[s].col, ci + k0a, nv * 4u, &S.full[s], policy);
                 }
                 bulk_g2s(S.st[s].rp, rp + r0a, nr * 4u, &S.full[s], policy);
             }
@@ -388,9 +398,12 @@ __global__ void __launch_bounds__(kSpmvThreads, CTAS)
         mbar_wait(&S.full[s], (it / STAGES) & 1);
         const SpmvStage<RPT, ColT> &T = S.st[s];
         const int32_t *srp = T.rp + (r0 & 3);
-        const int32_t base = (srp[0] & ~(G - 1));   // first staged element
-        const double *xt = x;
-        if (sizeof(ColT) == 2) xt += __ldg(tile_col0 + b);   // offsets count from the tile's column 0
+        int32_t c0 = -1;
+        if (kCol16) c0 = __ldg(tile_col0 + b);
+        const bool narrow = kCol16 && c0 >= 0;
+        const int32_t base = srp[0] & ~(narrow ? 7 : 3);   // first staged element
+        const double *xt = narrow ? x + c0 : x;            // offsets count from the tile's column 0
+        const uint16_t *col16 = reinterpret_cast<const uint16_t *>(T.col);
         int32_t k[RPT], e[RPT];
         double acc[RPT];
         bool more = false;
@@ -414,7 +427,7 @@ __global__ void __launch_bounds__(kSpmvThreads, CTAS)
 #pragma unroll
                 for (int i = 0; i < kSpmvChunk; ++i)
                     if (k[j] + i < e[j]) {
-                        xv[j][i] = __ldg(xt + T.col[k[j] + i]);
+                        xv[j][i] = __ldg(xt + (narrow ? (int32_t)col16[k[j] + i] : T.col[k[j] + i]));
                         vv[j][i] = T.val[k[j] + i];
                     }
             more = false;
@@ -475,7 +488,7 @@ __global__ void __launch_bounds__(kSpmvThreads, CTAS)
 }
 
 template <int EPI, int RPT, int STAGES, int CTAS, typename ColT>
-static void launch_spmv_tma_cols(const Ctx &ctx, const DeviceCsr &A, const ColT *cols, double alpha,
+static void launch_spmv_tma_cols(const Ctx &ctx, const DeviceCsr &A, double alpha,
                                  const double *x, double beta, const double *y_in, double *y_out,
                                  const double *dot_with, double *result, int32_t red_rows,
                                  const int32_t *stop)
@@ -493,7 +506,7 @@ static void launch_spmv_tma_cols(const Ctx &ctx, const DeviceCsr &A, const ColT 
     const int grid = std::min<int>(A.nblocks, ctx.num_sms * CTAS);
     csr_spmv_tma_kernel<EPI, RPT, STAGES, CTAS, ColT>
         <<<grid, kSpmvThreads, sizeof(Smem), ctx.stream>>>(
-            A.nblocks, A.blk_row, A.rp, cols, A.tile_col0, A.v, x, alpha, beta, y_in, y_out,
+            A.nblocks, A.blk_row, A.rp, A.ci, A.ci16, A.tile_col0, A.v, x, alpha, beta, y_in, y_out,
             dot_with, ctx.partials, ctx.tickets + 0, result, red_rows, stop);
 }
 
@@ -504,13 +517,11 @@ static void launch_spmv_tma_cfg(const Ctx &ctx, const DeviceCsr &A, double alpha
                                 const int32_t *stop)
 {
     if (A.ci16 != nullptr)
-        launch_spmv_tma_cols<EPI, RPT, STAGES, CTAS, uint16_t>(ctx, A, A.ci16, alpha, x, beta, y_in,
-                                                               y_out, dot_with, result, red_rows,
-                                                               stop);
+        launch_spmv_tma_cols<EPI, RPT, STAGES, CTAS, uint16_t>(ctx, A, alpha, x, beta, y_in, y_out,
+                                                               dot_with, result, red_rows, stop);
     else
-        launch_spmv_tma_cols<EPI, RPT, STAGES, CTAS, int32_t>(ctx, A, A.ci, alpha, x, beta, y_in,
-                                                              y_out, dot_with, result, red_rows,
-                                                              stop);
+        launch_spmv_tma_cols<EPI, RPT, STAGES, CTAS, int32_t>(ctx, A, alpha, x, beta, y_in, y_out,
+                                                              dot_with, result, red_rows, stop);
 }
 
 template <int EPI>

@@ -313,7 +313,7 @@ __global__ void __launch_bounds__(kSmallThreads, 1)
                 if (t < workers)
                     for (int32_t i = t; i < n; i += workers) {
                         double acc = 0.0;
-                        for (int32_t q = rp[i]; q < rp[i + 1]; ++q) acc += v[q] * vk[ci[q]];
+                        for (int32_t q = rp[i]; q < rp[i + 1]; ++q) acc = fma(v[q], vk[ci[q]], acc);
                         w[i] = acc;
                     }
             }
@@ -330,43 +330,56 @@ __global__ void __launch_bounds__(kSmallThreads, 1)
                 const double *v0 = V;
                 for (int32_t i = t; i < n; i += kSmallThreads) {
                     double acc = 0.0;
-                    for (int32_t q = rp[i]; q < rp[i + 1]; ++q) acc += v[q] * v0[ci[q]];
+                    for (int32_t q = rp[i]; q < rp[i + 1]; ++q) acc = fma(v[q], v0[ci[q]], acc);
                     w[i] = acc;
                 }
                 __syncthreads();
             }
             double *col = H + (size_t)k * (m + 1);
             for (int pass = 0; pass < 2; ++pass) {
-                for (int i = wid; i <= k; i += NW) {
-                    const double *vi = V + (size_t)i * n;
-                    double p0 = 0.0, p1 = 0.0, p2 = 0.0, p3 = 0.0;
+                // a warp takes the projections i = wid, wid + NW, ... two at a time: every
+                // element of w is read once for both, the partial sums are fused multiply-adds
+                for (int i = wid; i <= k; i += 2 * NW) {
+                    const int i2 = i + NW;
+                    const bool two = i2 <= k;
+                    const double *va = V + (size_t)i * n;
+                    const double *vb = V + (size_t)(two ? i2 : i) * n;
+                    double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
                     int32_t j = lane;
-                    for (; j + 96 < n; j += 128) {
-                        p0 += w[j] * vi[j];
-                        p1 += w[j + 32] * vi[j + 32];
-                        p2 += w[j + 64] * vi[j + 64];
-                        p3 += w[j + 96] * vi[j + 96];
+                    for (; j + 32 < n; j += 64) {
+                        const double w0 = w[j], w1 = w[j + 32];
+                        a0 = fma(w0, va[j], a0);
+                        a1 = fma(w1, va[j + 32], a1);
+                        b0 = fma(w0, vb[j], b0);
+                        b1 = fma(w1, vb[j + 32], b1);
                     }
-                    for (; j < n; j += 32) p0 += w[j] * vi[j];
-                    const double part = warp_sum((p0 + p1) + (p2 + p3));
-                    if (lane == 0) hbuf[i] = part;
+                    if (j < n) {
+                        const double w0 = w[j];
+                        a0 = fma(w0, va[j], a0);
+                        b0 = fma(w0, vb[j], b0);
+                    }
+                    const double pa = warp_sum(a0 + a1), pb = warp_sum(b0 + b1);
+                    if (lane == 0) {
+                        hbuf[i] = pa;
+                        if (two) hbuf[i2] = pb;
+                    }
                 }
                 __syncthreads();
                 for (int32_t j = t; j < n; j += kSmallThreads) {
                     double a0 = w[j], a1 = 0.0;
                     int i = 0;
                     for (; i + 1 <= k; i += 2) {
-                        a0 += (-hbuf[i]) * V[(size_t)i * n + j];
-                        a1 += (-hbuf[i + 1]) * V[(size_t)(i + 1) * n + j];
+                        a0 = fma(-hbuf[i], V[(size_t)i * n + j], a0);
+                        a1 = fma(-hbuf[i + 1], V[(size_t)(i + 1) * n + j], a1);
                     }
-                    if (i <= k) a0 += (-hbuf[i]) * V[(size_t)i * n + j];
+                    if (i <= k) a0 = fma(-hbuf[i], V[(size_t)i * n + j], a0);
                     w[j] = a0 + a1;
                 }
                 if (t <= k) col[t] = pass == 0 ? hbuf[t] : col[t] + hbuf[t];
                 __syncthreads();
             }
             double part = 0.0;
-            for (int32_t j = t; j < n; j += kSmallThreads) part += w[j] * w[j];
+            for (int32_t j = t; j < n; j += kSmallThreads) part = fma(w[j], w[j], part);
             const double hn = sqrt(cta_sum<kSmallThreads>(part, buf, phase));
             const double inv = hn != 0.0 ? 1.0 / hn : 0.0;
             double *vn = V + (size_t)(k + 1) * n;

@@ -70,6 +70,44 @@ def test_spmv_bit_exact_ragged_and_edge_cases(gpu, sz, orc):
         gpu.free(dx); gpu.free(dy); A.close()
 
 
+@pytest.mark.parametrize("col32", ["0", "1"])
+def test_spmv_compact_column_stream_mixed_tiles(sz, orc, monkeypatch, col32):
+    """the pipelined SpMV reads a row tile's columns as 16-bit offsets when they span < 2^16 and
+    as 32-bit indices otherwise, tile by tile: a banded matrix of 150 000 rows (narrow tiles)
+    whose last rows couple to both ends (wide tiles, as the overlap rows of a strip do), bit for
+    bit against the oracle with the compact stream on and off, incl. the fused reductions"""
+    if sz.device_count() < 1:
+        pytest.skip("no CUDA device")
+    monkeypatch.setenv("SCHWZ_B200_SPMV_COL32", col32)
+    import scipy.sparse as sp
+    rng = np.random.default_rng(9)
+    n = 150000
+    offs = [-900, -3, -1, 0, 1, 2, 700]
+    B = sp.diags([rng.standard_normal(n - abs(o)) for o in offs], offs, shape=(n, n), format="lil")
+    for r in range(n - 600, n):                       # wide rows: both ends of the index range
+        B[r, r - (n - 600)] = rng.standard_normal()
+        B[r, 70000 + (r % 1000)] = rng.standard_normal()
+    B = B.tocsr(); B.sort_indices()
+    rp, ci, v = B.indptr.astype(np.int32), B.indices.astype(np.int32), B.data
+    gpu = sz.Context(0)                               # the switch is read when a context is made
+    A = sz.Csr(gpu, rp, ci, v)
+    x = rng.standard_normal(n)
+    y0 = rng.standard_normal(n)
+    dx = gpu.to_device(x)
+    orc.set_threads(orc.max_threads())
+    try:
+        for alpha, beta in ((1.0, 0.0), (-1.0, 1.0)):
+            dy = gpu.to_device(y0)
+            A.spmv(dx, dy, alpha, beta)
+            assert np.array_equal(gpu.to_host(dy, n), orc.spmv(rp, ci, v, x, alpha, beta, y0))
+            gpu.free(dy)
+    finally:
+        orc.set_threads(1)
+    gpu.free(dx)
+    A.close()
+    gpu.close()
+
+
 def test_spmv_long_row_path(gpu, sz, orc):
     rng = np.random.default_rng(2)
     rp, ci, v = _rand_csr(rng, 40, 9000, 6, long_row=(17, 5000))   # > one CTA tile
