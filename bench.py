@@ -724,6 +724,11 @@ def run_b200(args):
                "dtype": "f64", "data": "synthetic", "config": workload(args),
                "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof,
                "cpu_baseline": cpu, "halo": halo, "wall_ms_per_step": 1e3 * wall / args.steps,
+               # host-blocking CUDA calls of the timed ras_run (rank 0): every stream
+               # synchronisation sits before the first / after the last enqueued iteration,
+               # the event waits look at a loop-state snapshot two chunks of iterations old
+               "host_waits": {"stream_syncs": res["host_stream_syncs"],
+                              "event_waits": res["host_event_waits"], "steps": args.steps},
                "global_resnorm": res["global_resnorm"], "impl": "b200"}
         if tts is not None:
             if cpu and cpu.get("tts_s_per_outer"):

@@ -412,6 +412,10 @@ typedef struct {
     int32_t converged;
     double global_resnorm, global_resnorm0;
     double elapsed_s;              /* steady_clock window of the reference */
+    /* host-blocking CUDA calls the loop made: stream synchronisations (all of them before the
+     * first / after the last iteration is enqueued) and event waits (one per subdomain per chunk
+     * of iterations, on a snapshot two chunks old) */
+    int32_t host_stream_syncs, host_event_waits;
 } schwz_loop_result;
 
 int schwz_b200_ras_run(schwz_ras **subdomains, int32_t n_local,

@@ -1085,6 +1085,8 @@ int schwz_b200_ras_run(schwz_ras **subs, int32_t n_local, const schwz_loop_optio
     res->global_resnorm = lr.global_resnorm;
     res->global_resnorm0 = lr.global_resnorm0;
     res->elapsed_s = lr.elapsed_s;
+    res->host_stream_syncs = lr.host_stream_syncs;
+    res->host_event_waits = lr.host_event_waits;
     ABI_END
 }
 

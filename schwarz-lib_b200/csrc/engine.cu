@@ -884,8 +884,10 @@ void ras_run(std::vector<Ras *> &subs, const LoopOptions &o, LoopResult &res,
     // entry: a subdomain that converged in an earlier call stays finished until it is reset
     std::vector<OuterState> st(nl);
     int alive = 0;
+    res.host_stream_syncs = res.host_event_waits = 0;
     for (int i = 0; i < nl; ++i) {
         subs[i]->fetch_state(st[i]);
+        ++res.host_stream_syncs;
         if (!st[i].stop) ++alive;
     }
     auto fill_result = [&](int iters_if_running) {
@@ -917,7 +919,10 @@ void ras_run(std::vector<Ras *> &subs, const LoopOptions &o, LoopResult &res,
         H.ctx->use();
         SCHWZ_CUDA(cudaMemsetAsync(H.history, 0, need * sizeof(double), H.ctx->stream));
     }
-    for (Ras *r : subs) r->ctx.sync();
+    for (Ras *r : subs) {
+        r->ctx.sync();
+        ++res.host_stream_syncs;
+    }
 
     const cudaStream_t hub_stream = H.ctx->stream;
     const double tol = o.tolerance;
@@ -1022,6 +1027,7 @@ void ras_run(std::vector<Ras *> &subs, const LoopOptions &o, LoopResult &res,
         for (int i = 0; i < nl; ++i) {
             subs[i]->ctx.use();
             SCHWZ_CUDA(cudaEventSynchronize(H.ev_chunk[slot][i]));
+            ++res.host_event_waits;
             const OuterState &S = H.pinned[(size_t)slot * nl + i];
             if (S.error != OUTER_OK) failed = true;
             if (S.stop) ++stopped;
@@ -1055,6 +1061,7 @@ void ras_run(std::vector<Ras *> &subs, const LoopOptions &o, LoopResult &res,
     if (multi_process) o.comm->ctx->sync();
     auto t1 = std::chrono::steady_clock::now();
     for (int i = 0; i < nl; ++i) subs[i]->fetch_state(st[i]);
+    res.host_stream_syncs += 2 * nl + 1 + (multi_process ? 1 : 0);
     if (history) {
         H.ctx->use();
         SCHWZ_CUDA(cudaMemcpyAsync(history, H.history, (size_t)o.max_iters * nl * sizeof(double),

@@ -383,6 +383,7 @@ struct LoopOptions {
 struct LoopResult {
     int32_t iters = 0, converged = 0;
     double global_resnorm = 0.0, global_resnorm0 = -1.0, elapsed_s = 0.0;
+    int32_t host_stream_syncs = 0, host_event_waits = 0;
 };
 void ras_run(std::vector<Ras *> &subs, const LoopOptions &opt, LoopResult &res,
              double *resnorm_history);

@@ -58,7 +58,8 @@ class LoopOptions(C.Structure):
 class LoopResult(C.Structure):
     _fields_ = [("iters", C.c_int32), ("converged", C.c_int32),
                 ("global_resnorm", C.c_double), ("global_resnorm0", C.c_double),
-                ("elapsed_s", C.c_double)]
+                ("elapsed_s", C.c_double), ("host_stream_syncs", C.c_int32),
+                ("host_event_waits", C.c_int32)]
 
 
 _lib = None
@@ -857,7 +858,8 @@ def ras_run(subs, num_subdomains, max_iters, tolerance=1e-6, enable_onesided=Fal
     hist = np.zeros((max_iters, len(subs))) if history else None
     _chk(load().schwz_b200_ras_run(arr, C.c_int32(len(subs)), C.byref(o), C.byref(res), _p(hist)))
     out = dict(iters=res.iters, converged=bool(res.converged), global_resnorm=res.global_resnorm,
-               global_resnorm0=res.global_resnorm0, elapsed_s=res.elapsed_s)
+               global_resnorm0=res.global_resnorm0, elapsed_s=res.elapsed_s,
+               host_stream_syncs=res.host_stream_syncs, host_event_waits=res.host_event_waits)
     if history:
         out["history"] = hist[:max(res.iters + (1 if res.converged else 0), 0)]
     return out
