@@ -18,6 +18,7 @@ bool g_use_cg_graph = true;   // SCHWZ_B200_NO_CG_GRAPH=1 turns the graph replay
 
 constexpr int kCgNoPoll = 160;   // up to this many iterations: enqueue all, never poll
 constexpr int kCgChunk = 32;     // otherwise poll the stop flag once per chunk
+constexpr int kCgWhileUnroll = 10;   // CG iterations per trip of the WHILE graph
 
 CgSolver::CgSolver(const Ctx &ctx, const DeviceCsr &A) : ctx_(ctx), A_(A), n_(A.nrows)
 {
@@ -102,14 +103,17 @@ void CgSolver::solve(const double *b, double *x, int32_t max_iters, double tol,
     //    Best for inexact local solves (local_tol = 0.1 stops after a handful of iterations).
     //    Also the only graph shape for budgets too long to unroll (local_max_iters = -1), which
     //    otherwise need the host to poll the stop flag.
-    // Measured on cfg2 (8 strips of 8.4 M rows on one B200): 83.8 ms per outer iteration as a
-    // WHILE graph against 83.4 - 84.5 ms unrolled at 50 iterations, 108.8 against 108.4 ms at 70
-    // (profiles/r2_while_graph.md) - the loop node costs nothing measurable, so it is the
-    // default; SCHWZ_B200_CG_WHILE=0 selects the unrolled graph (budgets up to kCgNoPoll).
+    // Measured (profiles/r2_while_graph.md): a trip of the loop node costs ~5 us.  With 8
+    // subdomain streams on one GPU that is invisible (cfg2: 83.8 ms per outer iteration as a WHILE
+    // graph against 83.4 - 84.5 unrolled), with one subdomain per GPU it is not (524 k rows, 50
+    // iterations: 1.38 against 1.13 ms; 2.1 M rows: 2.75 against 2.48).  So: a solve that its
+    // BUDGET will end (tight tolerance, at most kCgNoPoll iterations) is unrolled, everything
+    // else - inexact solves that stop on their tolerance, budgets too long to unroll - runs as a
+    // WHILE graph with kCgWhileUnroll iterations per trip.  SCHWZ_B200_CG_WHILE=0 / 1 forces one.
     const char *force_while_s = std::getenv("SCHWZ_B200_CG_WHILE");
     const int force_while = force_while_s ? std::atoi(force_while_s) : -1;
-    const bool as_while =
-        force_while >= 0 ? (force_while != 0 || max_iters > kCgNoPoll) : true;
+    const bool as_while = force_while >= 0 ? (force_while != 0 || max_iters > kCgNoPoll)
+                                           : (tol >= 1e-4 || max_iters > kCgNoPoll);
     // (the level-per-launch triangular solves of the ILU preconditioner are graphs of their
     // own and cannot be captured; the one-kernel solves can)
     const bool ilu_levels = M_ && M_->kind() == PRECOND_ILU && M_->uses_level_graphs();
@@ -175,7 +179,12 @@ void CgSolver::solve(const double *b, double *x, int32_t max_iters, double tol,
                     SCHWZ_CUDA(cudaStreamBeginCaptureToGraph(ctx_.stream, body, nullptr, nullptr, 0,
                                                              cudaStreamCaptureModeThreadLocal));
                     capturing = true;
-                    iteration(x, loop);
+                    // kCgWhileUnroll iterations per trip: a trip of the loop node costs ~5 us
+                    // (1.13 -> 1.38 ms per 50-iteration solve at 524 k rows with one iteration
+                    // per trip, profiles/r2_while_graph.md); iterations past the stop decision
+                    // inside a trip are no-ops and leave the loop condition alone
+                    for (int u = 0; u < std::min(kCgWhileUnroll, std::max(max_iters, 1)); ++u)
+                        iteration(x, loop);
                     cudaGraph_t ignored = nullptr;
                     SCHWZ_CUDA(cudaStreamEndCapture(ctx_.stream, &ignored));
                     capturing = false;
