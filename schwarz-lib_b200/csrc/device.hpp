@@ -84,6 +84,36 @@ struct DeviceCsr {
     ~DeviceCsr();
 };
 
+// Programmatic dependent launch inside a CG solve: while a PdlScope(true) is alive on this host
+// thread, the CG step kernels (x/p update, SpMV, r update, init, flush) are launched with
+// programmaticStreamSerializationAllowed: their CTAs become resident while the predecessor's
+// last CTAs still run and wait in cudaGridDependencySynchronize(), which every one of those
+// kernels executes before it touches anything - the kernel boundary shrinks from a drain +
+// launch + ramp to a hand-over.  SCHWZ_B200_CG_NO_PDL=1 turns it off.
+extern bool g_cg_pdl;
+extern thread_local bool t_pdl_launch;
+struct PdlScope {
+    bool prev;
+    explicit PdlScope(bool on) : prev(t_pdl_launch) { t_pdl_launch = on; }
+    ~PdlScope() { t_pdl_launch = prev; }
+};
+template <typename K, typename... Args>
+inline void launch_maybe_pdl(K kernel, dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                             Args... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = (t_pdl_launch && g_cg_pdl) ? 1 : 0;
+    SCHWZ_CUDA(cudaLaunchKernelEx(&cfg, kernel, args...));
+}
+
 extern bool g_spmv_col16;   // SCHWZ_B200_SPMV_COL32=1 turns the 16-bit column stream off
 extern bool g_force_simple_spmv;
 extern int g_spmv_variant;

@@ -15,6 +15,8 @@
 namespace schwz_b200 {
 
 std::atomic<int64_t> g_launches{0};
+bool g_cg_pdl = true;               // SCHWZ_B200_CG_NO_PDL=1: plain stream order inside a CG solve
+thread_local bool t_pdl_launch = false;
 bool g_spmv_col16 = true;           // SCHWZ_B200_SPMV_COL32=1: 32-bit column indices (A/B)
 bool g_force_simple_spmv = false;   // SCHWZ_B200_SIMPLE_SPMV=1: one-shot kernel (A/B measurements)
 int g_spmv_variant = 1;             // SCHWZ_B200_SPMV_VARIANT: launch shape of the pipelined kernel
@@ -337,6 +339,9 @@ __global__ void __launch_bounds__(kSpmvThreads, CTAS)
     extern __shared__ __align__(128) unsigned char smem_raw[];
     using Smem = SpmvSmem<RPT, STAGES, ColT>;
     Smem &S = *reinterpret_cast<Smem *>(smem_raw);
+    // (a no-op unless launched with programmatic stream serialisation: see PdlScope)
+    cudaGridDependencySynchronize();
+    cudaTriggerProgrammaticLaunchCompletion();
     if (stop != nullptr && *stop != 0) return;
     constexpr bool kCol16 = sizeof(ColT) == 2;
 
@@ -504,10 +509,12 @@ static void launch_spmv_tma_cols(const Ctx &ctx, const DeviceCsr &A, double alph
         configured[ctx.device].store(true, std::memory_order_release);
     }
     const int grid = std::min<int>(A.nblocks, ctx.num_sms * CTAS);
-    csr_spmv_tma_kernel<EPI, RPT, STAGES, CTAS, ColT>
-        <<<grid, kSpmvThreads, sizeof(Smem), ctx.stream>>>(
-            A.nblocks, A.blk_row, A.rp, A.ci, A.ci16, A.tile_col0, A.v, x, alpha, beta, y_in, y_out,
-            dot_with, ctx.partials, ctx.tickets + 0, result, red_rows, stop);
+    launch_maybe_pdl(csr_spmv_tma_kernel<EPI, RPT, STAGES, CTAS, ColT>, dim3(grid),
+                     dim3(kSpmvThreads), sizeof(Smem), ctx.stream, A.nblocks,
+                     (const int32_t *)A.blk_row, (const int32_t *)A.rp, (const int32_t *)A.ci,
+                     (const uint16_t *)A.ci16, (const int32_t *)A.tile_col0, (const double *)A.v, x,
+                     alpha, beta, y_in, y_out, dot_with, ctx.partials, ctx.tickets + 0, result,
+                     red_rows, stop);
 }
 
 template <int EPI, int RPT, int STAGES, int CTAS>
@@ -786,6 +793,8 @@ void launch_permute(const Ctx &ctx, int32_t n, const int32_t *perm, int inverse,
 __global__ void cg_init_kernel(CgScalars *s, int32_t max_iters, double tol,
                                const int32_t *outer_stop, cudaGraphConditionalHandle loop)
 {
+    cudaGridDependencySynchronize();
+    cudaTriggerProgrammaticLaunchCompletion();
     // s->rho already holds ||b - A x0||^2 (fused into the residual SpMV)
     const double r0 = sqrt(s->rho);
     s->r0 = r0;
@@ -808,7 +817,8 @@ void launch_cg_init(const Ctx &ctx, CgScalars *s, int32_t max_iters, double tol,
                     const int32_t *outer_stop, cudaGraphConditionalHandle loop)
 {
     ctx.use();
-    cg_init_kernel<<<1, 1, 0, ctx.stream>>>(s, max_iters, tol, outer_stop, loop);
+    launch_maybe_pdl(cg_init_kernel, dim3(1), dim3(1), 0, ctx.stream, s, max_iters, tol, outer_stop,
+                     loop);
     SCHWZ_CUDA(cudaGetLastError());
     count_launch();
 }
@@ -829,6 +839,8 @@ __global__ void __launch_bounds__(kBlock)
     cg_xp_update_kernel(int64_t n, const double *__restrict__ r, double *__restrict__ p,
                         double *__restrict__ x, const CgScalars *__restrict__ s)
 {
+    cudaGridDependencySynchronize();
+    cudaTriggerProgrammaticLaunchCompletion();
     if (s->stop) return;
     const bool fresh = (s->iter == 0) || (s->prev_rho == 0.0);
     const double t = fresh ? 0.0 : s->rho / s->prev_rho;
@@ -880,7 +892,8 @@ void launch_cg_xp_update(const Ctx &ctx, int64_t n, const double *r, double *p, 
                          const CgScalars *s)
 {
     ctx.use();
-    cg_xp_update_kernel<<<vec_grid(ctx, (n + 1) / 2), kBlock, 0, ctx.stream>>>(n, r, p, x, s);
+    launch_maybe_pdl(cg_xp_update_kernel, dim3(vec_grid(ctx, (n + 1) / 2)), dim3(kBlock), 0,
+                     ctx.stream, n, r, p, x, s);
     SCHWZ_CUDA(cudaGetLastError());
     count_launch();
 }
@@ -892,6 +905,8 @@ __global__ void __launch_bounds__(kBlock)
                        cudaGraphConditionalHandle loop)
 {
     __shared__ double s_warp[kBlock / 32];
+    cudaGridDependencySynchronize();
+    cudaTriggerProgrammaticLaunchCompletion();
     if (s->stop) return;
     const double rho = s->rho, beta = s->beta;
     const bool skip = (beta == 0.0);
@@ -958,8 +973,8 @@ void launch_cg_r_update(const Ctx &ctx, int64_t n, double *r, const double *q, C
                         bool precond, cudaGraphConditionalHandle loop)
 {
     ctx.use();
-    cg_r_update_kernel<<<vec_grid(ctx, (n + 1) / 2), kBlock, 0, ctx.stream>>>(
-        n, r, q, s, ctx.partials, ctx.tickets + 2, precond ? 1 : 0, loop);
+    launch_maybe_pdl(cg_r_update_kernel, dim3(vec_grid(ctx, (n + 1) / 2)), dim3(kBlock), 0,
+                     ctx.stream, n, r, q, s, ctx.partials, ctx.tickets + 2, precond ? 1 : 0, loop);
     SCHWZ_CUDA(cudaGetLastError());
     count_launch();
 }
@@ -969,6 +984,8 @@ __global__ void __launch_bounds__(kBlock)
     cg_flush_x_kernel(int64_t n, double *__restrict__ x, const double *__restrict__ p,
                       const CgScalars *__restrict__ s)
 {
+    cudaGridDependencySynchronize();
+    cudaTriggerProgrammaticLaunchCompletion();
     if (!s->pending) return;
     const double a = s->alpha;
     for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n;
@@ -979,7 +996,8 @@ __global__ void __launch_bounds__(kBlock)
 void launch_cg_flush_x(const Ctx &ctx, int64_t n, double *x, const double *p, const CgScalars *s)
 {
     ctx.use();
-    cg_flush_x_kernel<<<vec_grid(ctx, n), kBlock, 0, ctx.stream>>>(n, x, p, s);
+    launch_maybe_pdl(cg_flush_x_kernel, dim3(vec_grid(ctx, n)), dim3(kBlock), 0, ctx.stream, n, x,
+                     (const double *)p, s);
     SCHWZ_CUDA(cudaGetLastError());
     count_launch();
 }

@@ -86,9 +86,12 @@ void CgSolver::solve(const double *b, double *x, int32_t max_iters, double tol,
         return;
     }
     auto enqueue_all = [&]() {
-        // r = b - A x, rho = r.r fused
+        // r = b - A x, rho = r.r fused (behind a full dependency on whatever produced b and x;
+        // every later launch of the solve may overlap its predecessor's tail, see PdlScope -
+        // with a preconditioner in between its own kernels serialise as usual)
         launch_spmv(ctx_, A_, -1.0, x, 1.0, b, r_, EPI_NRM2SQ, nullptr, &s_->rho, (int32_t)n_,
                     outer_stop);
+        PdlScope pdl(true);
         launch_cg_init(ctx_, s_, max_iters, tol, outer_stop);
         for (int it = 0; it < max_iters; ++it) iteration(x);
         launch_cg_flush_x(ctx_, n_, x, p_, s_);
