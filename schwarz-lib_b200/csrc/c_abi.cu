@@ -74,8 +74,8 @@ int schwz_b200_ctx_create(int device, schwz_ctx **out)
     g_use_cg_graph = !(ng && ng[0] == '1');
     const char *c32 = std::getenv("SCHWZ_B200_SPMV_COL32");
     g_spmv_col16 = !(c32 && c32[0] == '1');
-    const char *cpdl = std::getenv("SCHWZ_B200_CG_NO_PDL");
-    g_cg_pdl = !(cpdl && cpdl[0] == '1');
+    const char *cpdl = std::getenv("SCHWZ_B200_CG_PDL");
+    g_cg_pdl = cpdl && cpdl[0] == '1';
     const char *npdl = std::getenv("SCHWZ_B200_TRS_NO_PDL");
     g_trs_pdl = !(npdl && npdl[0] == '1');
     const char *mgs = std::getenv("SCHWZ_B200_GMRES_MGS");

@@ -88,8 +88,11 @@ struct DeviceCsr {
 // thread, the CG step kernels (x/p update, SpMV, r update, init, flush) are launched with
 // programmaticStreamSerializationAllowed: their CTAs become resident while the predecessor's
 // last CTAs still run and wait in cudaGridDependencySynchronize(), which every one of those
-// kernels executes before it touches anything - the kernel boundary shrinks from a drain +
-// launch + ramp to a hand-over.  SCHWZ_B200_CG_NO_PDL=1 turns it off.
+// kernels executes before it touches anything.  MEASURED AND NOT KEPT AS THE DEFAULT
+// (profiles/r2_while_graph.md): unlike the triangular solves, whose kernels have a dependent
+// chain of loads to hide, these are full-width streaming kernels and the early-resident
+// successor only takes SM slots from the running one - 1.19 against 1.15 ms per 50-iteration
+// solve at 524 k rows, 10.47 against 9.41 ms at 8.4 M rows.  SCHWZ_B200_CG_PDL=1 turns it on.
 extern bool g_cg_pdl;
 extern thread_local bool t_pdl_launch;
 struct PdlScope {

@@ -532,14 +532,23 @@ void Ras::exchange_push(int32_t iter, bool repush)
             launch_halo_pack_push(ctx, no, out_off_, out_total_, out_src_, x, out_dst_dev_[0],
                                   nullptr, 0, stop, opt.use_mixed_precision != 0);
         } else {
-            // epochs count exchanges over the lifetime of the subdomain, so the
-            // loop may be entered repeatedly (warm-up + timed runs).  A push left over from
-            // the last ras_run (nobody has unpacked it) is rewritten, not followed by another.
-            if (tail_pending) {
-                repush = true;
+            // Epochs count exchanges over the lifetime of the subdomain, so the loop may be
+            // entered repeatedly (warm-up + timed runs).  Invariant: push_epoch_ is
+            // unpack_epoch_ or unpack_epoch_ + 1, and tail_pending <=> a push nobody has unpacked
+            // yet is out.  A real push REWRITES such a pending push (same epoch, same buffer,
+            // current x) instead of following it with another; a timing / refresh push
+            // (repush) rewrites the last epoch without changing what is pending - and becomes
+            // the pending push when none is out.
+            if (repush) {
+                if (push_epoch_ == unpack_epoch_) {
+                    ++push_epoch_;
+                    tail_pending = true;
+                }
+            } else if (tail_pending) {
                 tail_pending = false;
+            } else {
+                ++push_epoch_;
             }
-            if (!repush || push_epoch_ == 0) ++push_epoch_;
             launch_halo_pack_push(ctx, no, out_off_, out_total_, out_src_, x,
                                   out_dst_dev_[push_epoch_ & 1], out_flag_dev_,
                                   (unsigned long long)push_epoch_, stop,
@@ -828,8 +837,7 @@ void ras_refresh_halo(std::vector<Ras *> &subs, int32_t P)
     for (Ras *r : subs) {
         r->set_exchange_mode(EXCHANGE_PUT_GATHERED);
         r->set_onesided(false);
-        r->exchange_push(0, r->tail_pending);
-        r->tail_pending = false;
+        r->exchange_push(0);
     }
     for (Ras *r : subs) {
         bool remote = false;
@@ -1013,8 +1021,7 @@ void ras_run(std::vector<Ras *> &subs, const LoopOptions &o, LoopResult &res,
         for (Ras *r : subs) {
             // the exchange of iteration 0: x as it stands now (a push left over from the
             // previous call is rewritten with the same epoch)
-            r->exchange_push(0, r->tail_pending);
-            r->tail_pending = false;
+            r->exchange_push(0);
         }
     // iterations enqueued between two looks at the loop state (SCHWZ_B200_OUTER_CHUNK)
     const char *env_chunk_s = std::getenv("SCHWZ_B200_OUTER_CHUNK");

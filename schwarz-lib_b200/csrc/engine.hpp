@@ -271,8 +271,9 @@ public:
     // (stage-by-stage callers decide on the host).
     // Exchange epochs (synchronous Put-gathered mode): every push carries the next epoch into the
     // neighbours' receive buffer of that parity and publishes it; every unpack consumes the
-    // next epoch.  repush = write the LAST epoch again (same buffer, same flag value): what the
-    // outer loop does on entry when its previous call ended with a push nobody has unpacked.
+    // next epoch.  A push that follows one nobody has unpacked yet (the tail push of the previous
+    // ras_run) rewrites it: same epoch, same buffer, current x.  repush = a timing / refresh
+    // launch: writes the last epoch again without changing what is pending.
     // One-sided mode uses receive buffer 0 only and no flags: the receiver always sees the
     // freshest values, as with the reference's single recv_buffer.
     void exchange_push(int32_t iter, bool repush = false);

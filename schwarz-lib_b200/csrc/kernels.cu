@@ -15,7 +15,7 @@
 namespace schwz_b200 {
 
 std::atomic<int64_t> g_launches{0};
-bool g_cg_pdl = true;               // SCHWZ_B200_CG_NO_PDL=1: plain stream order inside a CG solve
+bool g_cg_pdl = false;              // SCHWZ_B200_CG_PDL=1: programmatic dependent launch inside a CG solve
 thread_local bool t_pdl_launch = false;
 bool g_spmv_col16 = true;           // SCHWZ_B200_SPMV_COL32=1: 32-bit column indices (A/B)
 bool g_force_simple_spmv = false;   // SCHWZ_B200_SIMPLE_SPMV=1: one-shot kernel (A/B measurements)
