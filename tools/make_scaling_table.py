@@ -11,7 +11,7 @@ import re
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 D = os.path.join(ROOT, "profiles", "r2_scaling")
-ORDER = ["cfg2_strips", "cfg2_blocks2d", "cfg2_inexact", "cfg2_tts_big", "cfg3_ani4", "cfg3_ani3",
+ORDER = ["cfg2_strips", "cfg2_blocks2d", "cfg2_2x2", "cfg2_inexact", "cfg2_tts_big", "cfg3_ani4", "cfg3_ani3",
          "cfg4_3d512_onesided"]
 rows = {}
 for f in glob.glob(os.path.join(D, "*.json")):

@@ -12,6 +12,8 @@ mkdir -p "$OUT"
 port=29700
 run() {
     name=$1; shift
+    # RUNS="cfg2_strips cfg3_ani4": only those
+    if [ -n "${RUNS:-}" ] && [[ " $RUNS " != *" $name "* ]]; then return; fi
     port=$((port + 1))
     if [ "$N" -gt 1 ]; then
         timeout ${TMO:-900} python -m torch.distributed.run --nnodes=1 --nproc-per-node "$N" \
@@ -23,6 +25,8 @@ run() {
     echo "$name rc=$?"
 }
 run cfg2_strips --steps 10 --warmup 3 --no-cpu-baseline --tts-size "$TTS"
+# the reference's own regular2d rule: 2 x 2 blocks (4 subdomains)
+run cfg2_2x2 --subdomains 4 --partition regular2d --steps 10 --warmup 3 --no-cpu-baseline --tts-size "$TTS"
 run cfg2_blocks2d --steps 10 --warmup 3 --no-cpu-baseline --partition regular2d --tts-size "$TTS"
 run cfg2_inexact --steps 10 --warmup 3 --no-cpu-baseline --tts-size 0 --local-tol 0.1 --local-iters 70
 run cfg3_ani4 --matrix ani4 --steps 100 --warmup 10 --no-cpu-baseline
@@ -32,7 +36,7 @@ if [ -n "${TTS_BIG:-}" ]; then
     # a to-tolerance run of the strips workload at TTS_BIG^2 (recorded as time_to_solution_full)
     TMO=1500 run cfg2_tts_big --size "$TTS_BIG" --steps 10 --warmup 3 --to-tolerance 200000 --tts-size 0 --no-cpu-baseline
 fi
-if [ "${SKIP_CFG5:-0}" != "1" ]; then
+if [ "${SKIP_CFG5:-0}" != "1" ] && { [ -z "${RUNS:-}" ] || [[ " $RUNS " == *" cfg5 "* ]]; }; then
     NUM_DEVICES=$N ONLY=cfg5 TMO=1500 tools/run_configs.sh "$OUT/bench_ras" > "$OUT/cfg5.log" 2>&1
     grep -E "Rank 0 |Time taken|relative residual|real" "$OUT/cfg5.log" | head -6
 fi
