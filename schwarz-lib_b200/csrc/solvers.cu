@@ -375,23 +375,11 @@ __global__ void __launch_bounds__(kBlock)
     }
 }
 
-// w -= h * v   (h is a device scalar)
-__global__ void __launch_bounds__(kBlock)
-    gmres_axpy_kernel(int64_t n, const double *h, double sign, const double *__restrict__ v,
-                      double *__restrict__ w, const GmresState *st)
-{
-    if (st->stop) return;
-    const double a = sign * (*h);
-    for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n;
-         i += (int64_t)gridDim.x * kBlock)
-        w[i] += a * v[i];
-}
-
 // One modified-Gram-Schmidt step fused with the NEXT projection: w -= h v (h a device scalar the
 // previous launch left), and in the same pass over w the dot product the next step needs -
 // w.v_next, or ||w|| after the last projection (v_next == nullptr).  Same operands, same
-// thread-to-element mapping and the same partial-sum tree as gmres_axpy_kernel followed by
-// gmres_dot_kernel, so the doubles are the same; w is streamed once instead of twice
+// thread-to-element mapping and the same partial-sum tree as a separate w += (-h) v pass followed
+// by gmres_dot_kernel (round 1), so the doubles are the same; w is streamed once instead of twice
 // (24 instead of 40 B/row per step) and a step is one launch instead of two.
 __global__ void __launch_bounds__(kBlock)
     gmres_axpy_dot_kernel(int64_t n, const double *h, const double *__restrict__ v,
