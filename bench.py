@@ -531,6 +531,10 @@ def run_b200(args):
     roof = {"bound": "hbm", "kernel": "csr_spmv_tma_kernel<EPI_DOT> (CG: q = A p, p.q fused)",
             "achieved": k0["GB/s"], "peak": peak, "unit": "GB/s", "frac": k0["GB/s"] / peak,
             "traffic": traffic, "peak_source": peak_src, "bytes_per_launch": k0["bytes"],
+            "traffic_note": "DRAM bytes per launch from ncu (profiles/spmv_traffic.json). Below the "
+                            "algorithmic bytes since round 2: narrow row tiles stream their columns "
+                            "as 16-bit offsets (10 instead of 12 B per non-zero); `achieved` keeps "
+                            "the algorithmic definition of SURVEY 8(d), so frac can read ~1.0",
             "launch_ms": k0["ms"],
             "share_of_step": per_step_spmv_ms / (ms / args.steps) if per_step_spmv_ms else None,
             "other_kernels": {k: v for k, v in kern.items() if k != "csr_spmv_tma_kernel<EPI_DOT>"}}

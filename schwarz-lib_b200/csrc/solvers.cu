@@ -633,13 +633,15 @@ void GmresSolver::result(int32_t *iters, double *resnorm, double *resnorm0)
 // i depends on; a wide level is one launch (a warp per row, lanes striding over
 // the row's entries, fixed-shape shuffle reduction; one thread per row for the
 // huge levels of 1..8-entry rows at the leaves), all launches of a solve in one
-// CUDA graph.  Runs of small levels - the dense separator triangles at the top
-// of a nested-dissection factor, a chain of 1..8-row levels holding most of
-// the non-zeros - are cut into blocks of <= 128 consecutive rows and solved as
-// x_K = Dinv_K (b_K - L[K, outside] x) with the explicit inverse of the block's
-// own triangle: two launches per block instead of one per level.
-// The solves are bound by the memory latency of a short dependent chain per
-// launch, not by bandwidth (tools/prof_trs.py).
+// CUDA graph with programmatic dependent launch between them (see trs_row).  Runs of
+// small levels - the dense separator triangles at the top of a nested-dissection
+// factor, a chain of 1..8-row levels holding most of the non-zeros - are cut into
+// blocks of <= 512 consecutive rows and solved as x_K = Dinv_K (b_K - L[K, outside] x)
+// with the explicit inverse of the block's own triangle: two launches per block
+// instead of one per level.  A second variant, the dependency-driven one-kernel
+// solve, follows further down (trs_flow_kernel); measurements of both in
+// profiles/r2_sptrsv.md.  The solves are bound by the length of their dependency
+// chain times the latency of a hop, not by bandwidth.
 // Algorithmic bytes: 12*nnz + 20*rows.
 // =============================================================================
 bool g_trs_pdl = true;   // SCHWZ_B200_TRS_NO_PDL=1: plain stream order between the level kernels
