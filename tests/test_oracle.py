@@ -206,3 +206,30 @@ def test_twosided_without_global_check_never_converges(orc):
     pb = orc.Problem(*orc.laplacian2d(8), 2)
     pb.configure(max_iters=60, enable_global_check=False)
     assert pb.run() == 60
+
+
+def test_rank_parallel_stepping_is_bit_identical(orc):
+    """bench.py's CPU arm steps the subdomains side by side (orc.set_rank_threads): every rank's
+    arithmetic is the same sequence as in the serial sweep, so iterates and residual histories
+    are identical doubles"""
+    import numpy as np
+    n, P = 96, 4
+    mat = orc.laplacian2d(n)
+
+    def run(rank_threads):
+        ob = orc.Problem(*mat, P)
+        ob.configure(tolerance=1e-8, local_tol=1e-12, local_max_iters=20, max_iters=100,
+                     enable_global_check=True)
+        orc.set_threads(1)
+        orc.set_rank_threads(rank_threads)
+        try:
+            for _ in range(6):
+                ob.step()
+        finally:
+            orc.set_rank_threads(1)
+        return [ob.history(r)[0] for r in range(P)], [ob.x(r) for r in range(P)]
+
+    h1, x1 = run(1)
+    h4, x4 = run(4)
+    for r in range(P):
+        assert np.array_equal(h1[r], h4[r]) and np.array_equal(x1[r], x4[r])
